@@ -1,0 +1,699 @@
+// C ABI (include/hfr.h): model handle (weights, activation arena, CUDA-graph cache), 1-NN handle, single-op entries.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <vector>
+
+#include "../../include/hfr.h"
+#include "graph.h"
+#include "launch.h"
+
+using namespace hfr;
+
+static thread_local std::string g_err;
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return HFR_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    const std::string m = e.what();
+    if (m.find("not found in graph") != std::string::npos) return HFR_ERR_NOT_FOUND;
+    if (m.rfind("graphdef:", 0) == 0 || m.rfind("hdf5:", 0) == 0) return HFR_ERR_FORMAT;
+    if (m.rfind("compile:", 0) == 0) return HFR_ERR_UNSUPPORTED;
+    return HFR_ERR_INVALID;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float f32_to_tf32(float f) {  // round to nearest even on the 13 dropped mantissa bits
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return f;
+  u += 0x0FFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cuda_check(cudaMalloc(&p, n), "cudaMalloc");
+    bytes = n;
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static void* upload(const void* host, size_t bytes) {
+  void* d = nullptr;
+  cuda_check(cudaMalloc(&d, bytes ? bytes : 4), "cudaMalloc(weights)");
+  if (bytes) cuda_check(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weights)");
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+struct LayerDev {
+  void* w = nullptr;      // kernel-ready weights
+  float* bias = nullptr;
+};
+
+struct GraphKey {
+  const void* x;
+  int in_dtype, batch, flags;
+  std::vector<void*> outs;
+  bool operator<(const GraphKey& o) const {
+    if (x != o.x) return x < o.x;
+    if (in_dtype != o.in_dtype) return in_dtype < o.in_dtype;
+    if (batch != o.batch) return batch < o.batch;
+    if (flags != o.flags) return flags < o.flags;
+    return outs < o.outs;
+  }
+};
+
+struct hfr_model {
+  Plan plan;
+  int device = -1, precision = HFR_BF16;
+  std::vector<LayerDev> dev;
+  // activation arena: per-image byte offsets of every value (multiplied by the batch at run time)
+  std::vector<size_t> val_off, val_bytes;
+  size_t per_image_bytes = 0;
+  bool keep_all = false;
+  DevBuf arena;
+  int last_batch = 0;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  // host-buffer path staging
+  DevBuf stage_in;
+  std::vector<std::unique_ptr<DevBuf>> stage_out;
+
+  ~hfr_model() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& d : dev) {
+      if (d.w) cudaFree(d.w);
+      if (d.bias) cudaFree(d.bias);
+    }
+  }
+
+  size_t value_image_bytes(int v) const {
+    const ValueInfo& vi = plan.values[(size_t)v];
+    const size_t n = (size_t)vi.H * vi.W * vi.C;
+    const size_t b = vi.is_vector ? n * 4 : n * elt_size(precision);
+    return (b + 255) / 256 * 256;
+  }
+
+  void plan_arena() {
+    const int nv = (int)plan.values.size();
+    val_off.assign((size_t)nv, 0);
+    val_bytes.assign((size_t)nv, 0);
+    struct Block { size_t off, size; };
+    std::vector<Block> free_list;
+    size_t top = 0;
+    auto alloc = [&](size_t sz) {
+      for (size_t i = 0; i < free_list.size(); ++i) {
+        if (free_list[i].size >= sz) {
+          size_t off = free_list[i].off;
+          free_list[i].off += sz;
+          free_list[i].size -= sz;
+          if (!free_list[i].size) free_list.erase(free_list.begin() + (long)i);
+          return off;
+        }
+      }
+      size_t off = top;
+      top += sz;
+      return off;
+    };
+    auto release = [&](size_t off, size_t sz) {
+      free_list.push_back({off, sz});
+      std::sort(free_list.begin(), free_list.end(), [](const Block& a, const Block& b) { return a.off < b.off; });
+      for (size_t i = 0; i + 1 < free_list.size();) {
+        if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+          free_list[i].size += free_list[i + 1].size;
+          free_list.erase(free_list.begin() + (long)i + 1);
+        } else {
+          ++i;
+        }
+      }
+    };
+    for (int li = 0; li < (int)plan.layers.size(); ++li) {
+      const Layer& L = plan.layers[(size_t)li];
+      val_bytes[(size_t)L.out] = value_image_bytes(L.out);
+      val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
+      if (keep_all) continue;
+      const int ins[2] = {L.in, L.in2};
+      for (int v : ins) {
+        if (v <= 0) continue;  // value 0 is the caller's input
+        if (plan.values[(size_t)v].last_use == li) release(val_off[(size_t)v], val_bytes[(size_t)v]);
+      }
+      if (plan.values[(size_t)L.out].last_use < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
+    }
+    per_image_bytes = top;
+  }
+
+  void upload_weights() {
+    // does any consumer of value v run on the tensor cores?  (tf32 mode: producers round their output to tf32)
+    dev.resize(plan.layers.size());
+    for (size_t i = 0; i < plan.layers.size(); ++i) {
+      const Layer& L = plan.layers[i];
+      LayerDev& d = dev[i];
+      if (!L.bias.empty()) d.bias = (float*)upload(L.bias.data(), L.bias.size() * 4);
+      if (L.w.empty()) continue;
+      const bool gemm_operand = (L.kind == L_PW || L.kind == L_CONV);
+      if (gemm_operand && precision == HFR_BF16) {
+        std::vector<uint16_t> h(L.w.size());
+        for (size_t j = 0; j < h.size(); ++j) h[j] = f32_to_bf16(L.w[j]);
+        d.w = upload(h.data(), h.size() * 2);
+      } else if (gemm_operand && precision == HFR_TF32) {
+        std::vector<float> h(L.w.size());
+        for (size_t j = 0; j < h.size(); ++j) h[j] = f32_to_tf32(L.w[j]);
+        d.w = upload(h.data(), h.size() * 4);
+      } else {
+        d.w = upload(L.w.data(), L.w.size() * 4);
+      }
+    }
+  }
+
+  bool feeds_tensor_core(int v) const {
+    for (const Layer& L : plan.layers)
+      if ((L.in == v) && (L.kind == L_PW || L.kind == L_CONV || L.kind == L_SUBSAMPLE)) return true;
+    return false;
+  }
+
+  void* val_ptr(int v, int batch) const { return (char*)arena.p + val_off[(size_t)v] * (size_t)batch; }
+
+  void ensure_arena(int batch) {
+    const size_t need = per_image_bytes * (size_t)batch;
+    if (need > arena.bytes) {
+      for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+      graphs.clear();
+      arena.ensure(need);
+    }
+  }
+
+  void run_layers(const void* x, int in_dtype, int batch, int flags, void* const* outs, cudaStream_t s) {
+    const int prec = precision;
+    const int rt = (prec == HFR_TF32);
+    for (size_t i = 0; i < plan.layers.size(); ++i) {
+      const Layer& L = plan.layers[i];
+      const LayerDev& d = dev[i];
+      const void* in = L.in == 0 ? x : val_ptr(L.in, batch);
+      void* out = val_ptr(L.out, batch);
+      const int act = L.act;  // A_NONE/A_RELU/A_RELU6 share values with the kernels' ACT_* codes
+      const int round_out = rt && feeds_tensor_core(L.out);
+      switch (L.kind) {
+        case L_STEM: {
+          StemArgs a;
+          memset(&a, 0, sizeof(a));
+          a.x = in; a.in_u8 = (in_dtype == HFR_IN_U8); a.w = (const float*)d.w; a.bias = d.bias; a.y = out;
+          a.B = batch; a.H = L.H; a.W = L.W; a.Ho = L.Ho; a.Wo = L.Wo; a.kh = L.kh; a.kw = L.kw; a.stride = L.stride;
+          a.pad_t = L.pad_t; a.pad_l = L.pad_l; a.cout = L.cout;
+          a.scale = 1.f;
+          if (a.in_u8) {
+            a.flip = (flags & HFR_FLAG_BGR) ? 1 : 0;
+            if (flags & HFR_FLAG_MEAN_IMAGENET) { a.mean[0] = 103.939f; a.mean[1] = 116.779f; a.mean[2] = 123.68f; }
+            if (flags & HFR_FLAG_MEAN_VGGFACE2) { a.mean[0] = 91.4953f; a.mean[1] = 103.8827f; a.mean[2] = 131.0912f; }
+            if (flags & HFR_FLAG_SCALE_PM1) { a.scale = 1.f / 127.5f; a.mean[0] = a.mean[1] = a.mean[2] = 1.f; }
+          }
+          a.act = act; a.round_tf32 = round_out;
+          launch_stem(a, prec, s);
+          break;
+        }
+        case L_DW: {
+          DwArgs a;
+          a.x = in; a.w = (const float*)d.w; a.bias = d.bias; a.y = out;
+          a.B = batch; a.H = L.H; a.W = L.W; a.C = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.stride = L.stride;
+          a.pad_t = L.pad_t; a.pad_l = L.pad_l; a.act = act; a.round_tf32 = round_out;
+          launch_dw(a, prec, s);
+          break;
+        }
+        case L_PW: {
+          GemmArgs a;
+          a.a = in; a.b = d.w; a.bias = d.bias;
+          a.residual = L.in2 >= 0 ? val_ptr(L.in2, batch) : nullptr;
+          a.y = out; a.M = (int64_t)batch * L.Ho * L.Wo; a.N = L.cout; a.K = L.cin;
+          a.act = act; a.round_tf32 = round_out;
+          launch_gemm(a, prec, device, s);
+          break;
+        }
+        case L_CONV: {
+          ConvArgs a;
+          a.x = in; a.w = d.w; a.bias = d.bias;
+          a.residual = L.in2 >= 0 ? val_ptr(L.in2, batch) : nullptr;
+          a.y = out; a.B = batch; a.H = L.H; a.W = L.W; a.cin = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.cout = L.cout;
+          a.kh = L.kh; a.kw = L.kw; a.stride = L.stride; a.pad_t = L.pad_t; a.pad_l = L.pad_l; a.dil = L.dil;
+          a.act = act; a.round_tf32 = round_out;
+          launch_conv(a, prec, device, s);
+          break;
+        }
+        case L_MAXPOOL: {
+          PoolArgs a;
+          a.x = in; a.y = out; a.B = batch; a.H = L.H; a.W = L.W; a.C = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.k = L.kh;
+          a.stride = L.stride; a.pad_t = L.pad_t; a.pad_l = L.pad_l; a.explicit_zero = L.explicit_zero_pad;
+          launch_maxpool(a, prec, s);
+          break;
+        }
+        case L_SUBSAMPLE:
+          launch_subsample(in, out, batch, L.H, L.W, L.cin, L.Ho, L.Wo, L.stride, prec, s);
+          break;
+        case L_GAP:
+          launch_gap(in, (float*)out, batch, L.H * L.W, L.cin, prec, s);
+          break;
+        case L_FC:
+          launch_fc((const float*)in, (const float*)d.w, d.bias, (float*)out, batch, L.cin, L.cout, act, s);
+          break;
+        default:
+          throw Error(HFR_ERR_UNSUPPORTED, "internal: unknown layer kind");
+      }
+    }
+    for (size_t o = 0; o < plan.outputs.size(); ++o) {
+      const int v = plan.outputs[o];
+      const ValueInfo& vi = plan.values[(size_t)v];
+      const int64_t dim = (int64_t)vi.H * vi.W * vi.C;
+      if (!vi.is_vector) {
+        launch_cast_to_f32(val_ptr(v, batch), (float*)outs[o], dim * batch, prec, s);
+        if (o == 0 && (flags & HFR_FLAG_L2NORM)) launch_l2norm((float*)outs[o], (float*)outs[o], batch, (int)dim, s);
+      } else if (o == 0 && (flags & HFR_FLAG_L2NORM)) {
+        launch_l2norm((const float*)val_ptr(v, batch), (float*)outs[o], batch, (int)dim, s);
+      } else {
+        cuda_check(cudaMemcpyAsync(outs[o], val_ptr(v, batch), (size_t)dim * batch * 4, cudaMemcpyDeviceToDevice, s),
+                   "cudaMemcpyAsync(output)");
+      }
+    }
+  }
+
+  void forward(const void* x, int in_dtype, int batch, int flags, void* const* outs, cudaStream_t s) {
+    if (device < 0) throw Error(HFR_ERR_STATE, "model was loaded host-only (device < 0); forward needs a GPU handle");
+    if (batch <= 0) throw Error(HFR_ERR_INVALID, "batch must be positive");
+    if (in_dtype != HFR_IN_F32 && in_dtype != HFR_IN_U8) throw Error(HFR_ERR_INVALID, "bad input dtype");
+    use_device(device);
+    ensure_arena(batch);
+    last_batch = batch;
+    if (!(flags & HFR_FLAG_CUDA_GRAPH) || s == nullptr) {
+      run_layers(x, in_dtype, batch, flags, outs, s);
+      return;
+    }
+    GraphKey key{x, in_dtype, batch, flags, std::vector<void*>(outs, outs + plan.outputs.size())};
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      if (graphs.size() >= 16) {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+      }
+      run_layers(x, in_dtype, batch, flags, outs, s);  // eager first pass: configures kernels, validates arguments
+      cudaGraph_t g = nullptr;
+      cuda_check(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+      try {
+        run_layers(x, in_dtype, batch, flags, outs, s);
+      } catch (...) {
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      cuda_check(cudaStreamEndCapture(s, &g), "cudaStreamEndCapture");
+      cudaGraphExec_t ge = nullptr;
+      cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      cuda_check(e, "cudaGraphInstantiate");
+      graphs[key] = ge;
+      return;  // the eager pass already produced this step's result
+    }
+    cuda_check(cudaGraphLaunch(it->second, s), "cudaGraphLaunch");
+  }
+};
+
+static std::vector<uint8_t> read_file(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(HFR_ERR_IO, std::string("cannot open '") + path + "'");
+  f.seekg(0, std::ios::end);
+  std::streamoff n = f.tellg();
+  f.seekg(0);
+  std::vector<uint8_t> data((size_t)n);
+  if (n && !f.read((char*)data.data(), n)) throw Error(HFR_ERR_IO, std::string("cannot read '") + path + "'");
+  return data;
+}
+
+extern "C" {
+
+const char* hfr_last_error(void) { return g_err.c_str(); }
+int hfr_version(void) { return 100; }
+int64_t hfr_launch_count(void) { return launch_count(); }
+
+int hfr_model_load(const char* path, const char* input_name, const char* output_names_csv, const char* phase_name,
+                   float phase_value, int input_hw, int device, int precision, hfr_model** out) {
+  return guarded([&] {
+    if (!path || !out) throw Error(HFR_ERR_INVALID, "null argument");
+    if (precision < HFR_FP32 || precision > HFR_BF16) throw Error(HFR_ERR_INVALID, "bad precision");
+    std::vector<uint8_t> data = read_file(path);
+    std::unique_ptr<hfr_model> m(new hfr_model());
+    m->precision = precision;
+    m->device = device;
+    static const uint8_t kHdf5Magic[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (data.size() >= 8 && memcmp(data.data(), kHdf5Magic, 8) == 0) {
+      m->plan = compile_keras_mobilenet_h5(data.data(), data.size(), input_hw);
+    } else {
+      if (!input_name || !output_names_csv) throw Error(HFR_ERR_INVALID, "input/output tensor names are required");
+      Graph g;
+      parse_graphdef(data.data(), data.size(), &g);
+      CompileOptions opt;
+      opt.input_name = input_name;
+      std::stringstream ss(output_names_csv);
+      std::string tok;
+      while (std::getline(ss, tok, ',')) {
+        while (!tok.empty() && tok.front() == ' ') tok.erase(tok.begin());
+        while (!tok.empty() && tok.back() == ' ') tok.pop_back();
+        if (!tok.empty()) opt.output_names.push_back(tok);
+      }
+      if (phase_name && *phase_name) opt.phase_name = phase_name;
+      opt.phase_value = phase_value;
+      opt.override_hw = input_hw;
+      m->plan = compile_graph(g, opt);
+    }
+    m->plan_arena();
+    if (device >= 0) {
+      use_device(device);
+      m->upload_weights();
+    }
+    *out = m.release();
+  });
+}
+
+int hfr_model_info(const hfr_model* m, int* in_h, int* in_w, int* in_c, int* n_outputs, int* out_dims) {
+  return guarded([&] {
+    if (!m) throw Error(HFR_ERR_INVALID, "null model");
+    if (in_h) *in_h = m->plan.in_h;
+    if (in_w) *in_w = m->plan.in_w;
+    if (in_c) *in_c = m->plan.in_c;
+    if (n_outputs) *n_outputs = (int)m->plan.outputs.size();
+    if (out_dims)
+      for (size_t i = 0; i < m->plan.outputs.size(); ++i) {
+        const ValueInfo& v = m->plan.values[(size_t)m->plan.outputs[i]];
+        out_dims[i] = v.H * v.W * v.C;
+      }
+  });
+}
+
+int64_t hfr_model_plan_json(const hfr_model* m, char* buf, int64_t buf_len) {
+  if (!m) return HFR_ERR_INVALID;
+  std::string js = m->plan.to_json();
+  js.insert(js.size() - 1, ",\"arena_bytes_per_image\":" + std::to_string(m->per_image_bytes) +
+                               ",\"precision\":" + std::to_string(m->precision));
+  if (buf && buf_len > (int64_t)js.size()) memcpy(buf, js.c_str(), js.size() + 1);
+  return (int64_t)js.size() + 1;
+}
+
+int64_t hfr_model_layer_weights(const hfr_model* m, int layer, float* w, int64_t w_cap, float* bias, int64_t b_cap) {
+  if (!m || layer < 0 || layer >= (int)m->plan.layers.size()) return HFR_ERR_INVALID;
+  const Layer& L = m->plan.layers[(size_t)layer];
+  if (w && w_cap >= (int64_t)L.w.size()) memcpy(w, L.w.data(), L.w.size() * 4);
+  if (bias && b_cap >= (int64_t)L.bias.size()) memcpy(bias, L.bias.data(), L.bias.size() * 4);
+  return (int64_t)L.w.size();
+}
+
+int hfr_model_forward(hfr_model* m, const void* x, int in_dtype, int batch, int flags, void* const* outs, void* stream) {
+  return guarded([&] {
+    if (!m || !x || !outs) throw Error(HFR_ERR_INVALID, "null argument");
+    m->forward(x, in_dtype, batch, flags, outs, (cudaStream_t)stream);
+  });
+}
+
+int hfr_model_forward_host(hfr_model* m, const void* x_host, int in_dtype, int batch, int flags, void* const* outs_host,
+                           void* stream) {
+  return guarded([&] {
+    if (!m || !x_host || !outs_host) throw Error(HFR_ERR_INVALID, "null argument");
+    if (m->device < 0) throw Error(HFR_ERR_STATE, "model was loaded host-only");
+    if (batch <= 0) throw Error(HFR_ERR_INVALID, "batch must be positive");
+    use_device(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t in_bytes =
+        (size_t)batch * m->plan.in_h * m->plan.in_w * m->plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);
+    m->stage_in.ensure(in_bytes);
+    const size_t no = m->plan.outputs.size();
+    if (m->stage_out.size() < no)
+      for (size_t i = m->stage_out.size(); i < no; ++i) m->stage_out.emplace_back(new DevBuf());
+    std::vector<void*> douts(no);
+    std::vector<size_t> obytes(no);
+    for (size_t i = 0; i < no; ++i) {
+      const ValueInfo& v = m->plan.values[(size_t)m->plan.outputs[i]];
+      obytes[i] = (size_t)batch * v.H * v.W * v.C * 4;
+      m->stage_out[i]->ensure(obytes[i]);
+      douts[i] = m->stage_out[i]->p;
+    }
+    cuda_check(cudaMemcpyAsync(m->stage_in.p, x_host, in_bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(H2D)");
+    m->forward(m->stage_in.p, in_dtype, batch, flags, douts.data(), s);
+    for (size_t i = 0; i < no; ++i)
+      cuda_check(cudaMemcpyAsync(outs_host[i], douts[i], obytes[i], cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(D2H)");
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  });
+}
+
+int hfr_model_set_keep_activations(hfr_model* m, int keep) {
+  return guarded([&] {
+    if (!m) throw Error(HFR_ERR_INVALID, "null model");
+    m->keep_all = keep != 0;
+    m->plan_arena();
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+    m->graphs.clear();
+  });
+}
+
+int64_t hfr_model_debug_layer(hfr_model* m, int layer_index, int batch, float* dst, void* stream) {
+  int64_t n = 0;
+  int rc = guarded([&] {
+    if (!m || !dst) throw Error(HFR_ERR_INVALID, "null argument");
+    if (!m->keep_all) throw Error(HFR_ERR_STATE, "call hfr_model_set_keep_activations(m, 1) before forward");
+    if (layer_index < 0 || layer_index >= (int)m->plan.layers.size()) throw Error(HFR_ERR_INVALID, "bad layer index");
+    if (batch != m->last_batch) throw Error(HFR_ERR_STATE, "batch does not match the last forward");
+    const int v = m->plan.layers[(size_t)layer_index].out;
+    const ValueInfo& vi = m->plan.values[(size_t)v];
+    n = (int64_t)vi.H * vi.W * vi.C;
+    use_device(m->device);
+    if (vi.is_vector)
+      cuda_check(cudaMemcpyAsync(dst, m->val_ptr(v, batch), (size_t)n * batch * 4, cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream), "cudaMemcpyAsync");
+    else
+      launch_cast_to_f32(m->val_ptr(v, batch), dst, n * batch, m->precision, (cudaStream_t)stream);
+  });
+  return rc < 0 ? rc : n;
+}
+
+void hfr_model_free(hfr_model* m) { delete m; }
+
+int hfr_age_gender_post(const float* age_probs, int batch, int n, float* age_out, int device, void* stream) {
+  return guarded([&] {
+    if (!age_probs || !age_out || batch <= 0 || n < 2) throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_age_post(age_probs, age_out, batch, n, (cudaStream_t)stream);
+  });
+}
+
+int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, void* stream) {
+  return guarded([&] {
+    if (!x || !y || n < 0 || dim <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_l2norm(x, y, n, dim, (cudaStream_t)stream);
+  });
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ 1-NN
+struct hfr_knn {
+  int device = 0, dim = 0, precision = HFR_BF16;
+  const float* gallery = nullptr;  // borrowed fp32 rows
+  int64_t n_local = 0, row_offset = 0;
+  DevBuf g_lowp, g_norm, q_lowp, part_score, part_idx;
+  DevBuf h_q, h_dist, h_idx;  // host-path staging
+};
+
+extern "C" {
+
+int hfr_knn_create(int device, int dim, int precision, hfr_knn** out) {
+  return guarded([&] {
+    if (!out) throw Error(HFR_ERR_INVALID, "null argument");
+    if (precision != HFR_TF32 && precision != HFR_BF16) throw Error(HFR_ERR_INVALID, "1-NN precision must be tf32 or bf16");
+    if (dim <= 0 || dim % 8) throw Error(HFR_ERR_INVALID, "1-NN dimension must be a positive multiple of 8");
+    use_device(device);
+    hfr_knn* k = new hfr_knn();
+    k->device = device;
+    k->dim = dim;
+    k->precision = precision;
+    *out = k;
+  });
+}
+
+int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64_t global_row_offset, void* stream) {
+  return guarded([&] {
+    if (!k || !gallery || n_local <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(k->device);
+    k->gallery = gallery;
+    k->n_local = n_local;
+    k->row_offset = global_row_offset;
+    k->g_norm.ensure((size_t)n_local * 4);
+    void* lowp = nullptr;
+    if (k->precision == HFR_BF16) {
+      k->g_lowp.ensure((size_t)n_local * k->dim * 2);
+      lowp = k->g_lowp.p;
+    }
+    launch_rows_prep(gallery, lowp, (float*)k->g_norm.p, n_local, k->dim, (cudaStream_t)stream);
+  });
+}
+
+int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist2, int64_t* best_idx, void* stream) {
+  return guarded([&] {
+    if (!k || !queries || !best_dist2 || !best_idx || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!k->gallery) throw Error(HFR_ERR_STATE, "hfr_knn_query before hfr_knn_set_gallery (NotFittedError)");
+    if (nq == 0) return;
+    use_device(k->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int splits, per;
+    knn_plan(nq, k->n_local, &splits, &per);
+    k->part_score.ensure((size_t)nq * splits * 2 * 4);
+    k->part_idx.ensure((size_t)nq * splits * 2 * 4);
+    KnnGemmArgs a;
+    a.nq = nq; a.n = k->n_local; a.d = k->dim; a.splits = splits; a.n_blocks_per_unit = per;
+    a.gnorm = (const float*)k->g_norm.p;
+    a.part_score = (float*)k->part_score.p;
+    a.part_idx = (int*)k->part_idx.p;
+    if (k->precision == HFR_BF16) {
+      k->q_lowp.ensure((size_t)nq * k->dim * 2);
+      launch_rows_prep(queries, k->q_lowp.p, nullptr, nq, k->dim, s);
+      a.q = k->q_lowp.p;
+      a.g = k->g_lowp.p;
+    } else {
+      a.q = queries;
+      a.g = k->gallery;
+    }
+    launch_knn_gemm(a, k->precision, k->device, s);
+    launch_knn_finalize(queries, k->gallery, a.part_score, a.part_idx, splits, nq, k->dim, k->row_offset, best_dist2,
+                        best_idx, s);
+  });
+}
+
+int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host,
+                       int64_t* best_idx_host, void* stream) {
+  int rc = guarded([&] {
+    if (!k || !queries_host || !best_dist2_host || !best_idx_host || nq <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(k->device);
+    k->h_q.ensure((size_t)nq * k->dim * 4);
+    k->h_dist.ensure((size_t)nq * 4);
+    k->h_idx.ensure((size_t)nq * 8);
+    cuda_check(cudaMemcpyAsync(k->h_q.p, queries_host, (size_t)nq * k->dim * 4, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream), "cudaMemcpyAsync(H2D)");
+  });
+  if (rc) return rc;
+  rc = hfr_knn_query(k, (const float*)k->h_q.p, nq, (float*)k->h_dist.p, (int64_t*)k->h_idx.p, stream);
+  if (rc) return rc;
+  return guarded([&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    cuda_check(cudaMemcpyAsync(best_dist2_host, k->h_dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_check(cudaMemcpyAsync(best_idx_host, k->h_idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  });
+}
+
+int hfr_knn_merge(const float* dist_all, const int64_t* idx_all, int n_parts, int64_t nq, float* best_dist2,
+                  int64_t* best_idx, int device, void* stream) {
+  return guarded([&] {
+    if (!dist_all || !idx_all || !best_dist2 || !best_idx || n_parts <= 0 || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_knn_merge(dist_all, idx_all, n_parts, nq, best_dist2, best_idx, (cudaStream_t)stream);
+  });
+}
+
+void hfr_knn_free(hfr_knn* k) { delete k; }
+
+// ------------------------------------------------------------------------------------------------ single operators
+int hfr_op_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int batch, int h, int w, int c,
+                     int stride, int pad_t, int pad_l, int ho, int wo, int act, int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    DwArgs a;
+    a.x = x; a.w = w9c; a.bias = bias; a.y = y; a.B = batch; a.H = h; a.W = w; a.C = c; a.Ho = ho; a.Wo = wo;
+    a.stride = stride; a.pad_t = pad_t; a.pad_l = pad_l; a.act = act; a.round_tf32 = 0;
+    launch_dw(a, dtype, (cudaStream_t)stream);
+  });
+}
+
+int hfr_op_gemm_bias_act(const void* a_, const void* b, const float* bias, const void* residual, void* y, int64_t m,
+                         int n, int k, int act, int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    GemmArgs a;
+    a.a = a_; a.b = b; a.bias = bias; a.residual = residual; a.y = y; a.M = m; a.N = n; a.K = k; a.act = act;
+    a.round_tf32 = 0;
+    launch_gemm(a, dtype, device, (cudaStream_t)stream);
+  });
+}
+
+int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* bias, void* y, int batch, int h, int w_,
+                     int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act,
+                     int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    StemArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.in_u8 = (in_dtype == HFR_IN_U8); a.w = w; a.bias = bias; a.y = y; a.B = batch; a.H = h; a.W = w_;
+    a.Ho = ho; a.Wo = wo; a.kh = kh; a.kw = kw; a.stride = stride; a.pad_t = pad_t; a.pad_l = pad_l; a.cout = cout;
+    a.scale = 1.f;
+    if (a.in_u8) {
+      a.flip = (flags & HFR_FLAG_BGR) ? 1 : 0;
+      if (flags & HFR_FLAG_MEAN_IMAGENET) { a.mean[0] = 103.939f; a.mean[1] = 116.779f; a.mean[2] = 123.68f; }
+      if (flags & HFR_FLAG_MEAN_VGGFACE2) { a.mean[0] = 91.4953f; a.mean[1] = 103.8827f; a.mean[2] = 131.0912f; }
+      if (flags & HFR_FLAG_SCALE_PM1) { a.scale = 1.f / 127.5f; a.mean[0] = a.mean[1] = a.mean[2] = 1.f; }
+    }
+    a.act = act;
+    launch_stem(a, dtype, (cudaStream_t)stream);
+  });
+}
+
+int hfr_op_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int batch, int h,
+                  int w_, int cin, int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int act,
+                  int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    ConvArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.residual = residual; a.y = y; a.B = batch; a.H = h; a.W = w_; a.cin = cin;
+    a.Ho = ho; a.Wo = wo; a.cout = cout; a.kh = kh; a.kw = kw; a.stride = stride; a.pad_t = pad_t; a.pad_l = pad_l;
+    a.dil = 1; a.act = act; a.round_tf32 = 0;
+    launch_conv(a, dtype, device, (cudaStream_t)stream);
+  });
+}
+
+int hfr_op_maxpool(const void* x, void* y, int batch, int h, int w, int c, int k, int stride, int pad_t, int pad_l,
+                   int ho, int wo, int explicit_zero, int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    PoolArgs a;
+    a.x = x; a.y = y; a.B = batch; a.H = h; a.W = w; a.C = c; a.Ho = ho; a.Wo = wo; a.k = k; a.stride = stride;
+    a.pad_t = pad_t; a.pad_l = pad_l; a.explicit_zero = explicit_zero;
+    launch_maxpool(a, dtype, (cudaStream_t)stream);
+  });
+}
+
+}  // extern "C"

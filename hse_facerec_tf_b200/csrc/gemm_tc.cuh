@@ -1,0 +1,368 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:   acc[M,N] = A[M,K] * B[N,K]^T   (both operands K-major)
+//
+//   warp 0 (1 lane)  TMA producer: A/B k-blocks (128-byte rows, SWIZZLE_128B) into a STAGES-deep smem ring
+//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma cta_group::1, M=128 x N=BLOCK_N, fp32 accumulators in TMEM (2 stages)
+//   warp 2           TMEM allocator
+//   warps 4..7       epilogue:     tcgen05.ld -> registers -> fused epilogue
+//
+// Epilogues
+//   EPI_STORE  out = act(acc + bias[n] (+ residual[m,n]))  -> T, staged in swizzled smem, written with TMA stores.
+//              Used by the 1x1 pointwise convolutions (A = NHWC activations viewed as [B*H*W, Cin]) and, with the
+//              im2col producer, by the 3x3 / 7x7 convolutions.
+//   EPI_KNN    score = gnorm[n] - 2*acc; running per-row top-2 over the unit's gallery range, written once per unit.
+//
+// Reference semantics being replaced: TF Conv2D(1x1)+Add+ReLU6 nodes `conv_pw_N*` of the frozen graph
+// (facerec_test.py:120 sess.run) and sklearn's ArgKmin euclidean reduction (facerec_test.py:272,284-285).
+#pragma once
+#include "ptx.cuh"
+
+namespace hfr {
+
+enum { EPI_STORE = 0, EPI_KNN = 1 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };
+enum { AMODE_2D = 0, AMODE_IM2COL = 1 };
+
+struct GemmParams {
+  int M, N, K;            // K in elements
+  int num_m_blocks;       // ceil(M/128)
+  int num_n_blocks;       // ceil(N/BLOCK_N)
+  int n_blocks_per_unit;  // STORE: 1.  KNN: gallery n-blocks handled by one work unit
+  int num_units;          // num_m_blocks * ceil(num_n_blocks / n_blocks_per_unit)
+  // EPI_STORE
+  const float* bias;      // [N] or nullptr
+  const void* residual;   // [M,N] of T or nullptr
+  int act;
+  int round_tf32;         // round stored fp32 values to tf32 (they feed the next tf32 GEMM)
+  // EPI_KNN
+  const float* gnorm;     // [N] squared norms of the gallery rows
+  float* part_score;      // [M][splits][2]
+  int* part_idx;          // [M][splits][2]
+  int splits;
+  // AMODE_IM2COL (implicit GEMM over an NHWC tensor): k-block kb -> (tap, channel block)
+  int conv_kw, conv_cblocks;   // taps along W, channel blocks (of BK elements) per tap
+  int conv_wo, conv_ho;        // output width/height: m -> (n, ho, wo)
+  int conv_stride, conv_pad_w, conv_pad_h, conv_dil;
+};
+
+template <typename T>
+struct GemmTraits;
+template <>
+struct GemmTraits<__nv_bfloat16> {
+  static constexpr bool kTF32 = false;
+  static constexpr uint32_t kFmt = 1;
+  static constexpr int BK = 64;  // elements per 128-byte row
+};
+template <>
+struct GemmTraits<float> {
+  static constexpr bool kTF32 = true;
+  static constexpr uint32_t kFmt = 2;
+  static constexpr int BK = 32;
+};
+
+template <int BLOCK_N, int EPI>
+struct GemmSmem {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBytes = (EPI == EPI_STORE) ? 2 * 128 * 128 : 2 * BLOCK_N * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kEpiBytes;
+  static constexpr int kStagesMax = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesMax > 6 ? 6 : kStagesMax;
+  static constexpr int kTotal = 1024 + kStages * kStageBytes + kEpiBytes + 256;
+};
+
+template <typename T, int BLOCK_N, int EPI, int AMODE>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using TR = GemmTraits<T>;
+  using SM = GemmSmem<BLOCK_N, EPI>;
+  constexpr int STAGES = SM::kStages;
+  constexpr int BK = TR::BK;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * SM::kABytes;
+  const uint32_t sEpi = smem_base + STAGES * SM::kStageBytes;
+  uint8_t* sEpi_gen = smem_gen + STAGES * SM::kStageBytes;
+  const uint32_t sBar = sEpi + SM::kEpiBytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sEpi_gen + SM::kEpiBytes + 192);
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 64u + 8u * s; };
+  auto tfull_bar = [&](int s) { return sBar + 128u + 8u * s; };
+  auto tempty_bar = [&](int s) { return sBar + 144u + 8u * s; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI == EPI_STORE) tma_prefetch_desc(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = (AMODE == AMODE_IM2COL) ? p.conv_kw * p.conv_kw * p.conv_cblocks : (p.K + BK - 1) / BK;
+  const int units_n = (p.num_n_blocks + p.n_blocks_per_unit - 1) / p.n_blocks_per_unit;
+
+  // unit -> (m block, first n block, n block count).  STORE: n fastest (neighbouring CTAs share the A tile in L2).
+  // KNN: m fastest (all CTAs sweep the same gallery range while it is L2-resident).
+  auto decode = [&](int u, int& mb, int& nb0, int& nbn) {
+    if (EPI == EPI_STORE) {
+      mb = u / units_n;
+      nb0 = u % units_n;
+      nbn = 1;
+    } else {
+      mb = u % p.num_m_blocks;
+      int sp = u / p.num_m_blocks;
+      nb0 = sp * p.n_blocks_per_unit;
+      nbn = min(p.n_blocks_per_unit, p.num_n_blocks - nb0);
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int mb, nb0, nbn;
+        decode(u, mb, nb0, nbn);
+        int im_n = 0, im_h = 0, im_w = 0;
+        if (AMODE == AMODE_IM2COL) {
+          int m0 = mb * 128;
+          im_w = m0 % p.conv_wo;
+          int t = m0 / p.conv_wo;
+          im_h = t % p.conv_ho;
+          im_n = t / p.conv_ho;
+        }
+        for (int nb = nb0; nb < nb0 + nbn; ++nb) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), SM::kStageBytes);
+            if (AMODE == AMODE_IM2COL) {
+              int tap = kb / p.conv_cblocks;
+              int cb = kb - tap * p.conv_cblocks;
+              int r = tap / p.conv_kw, s = tap - r * p.conv_kw;
+              tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
+                                 im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
+                                 (uint16_t)(s * p.conv_dil), (uint16_t)(r * p.conv_dil));
+            } else {
+              tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
+            }
+            tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(TR::kFmt, 128, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int mb, nb0, nbn;
+        decode(u, mb, nb0, nbn);
+        for (int nb = nb0; nb < nb0 + nbn; ++nb, ++tile) {
+          const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+          mbar_wait(tempty_bar(as), aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(sA + stage * SM::kABytes);
+            const uint64_t bdesc = umma_desc_sw128(sB + stage * SM::kBBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte swizzle row
+              umma<TR::kTF32>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int ew = warp - 4;           // == warp % 4: TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;    // row within the 128-row tile
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    uint32_t tile = 0;
+    if constexpr (EPI == EPI_STORE) {
+      constexpr int CH_ELEMS = 128 / (int)sizeof(T);  // columns per 128-byte staging chunk (32 fp32 / 64 bf16)
+      constexpr int NCHUNK = BLOCK_N / CH_ELEMS;
+      uint32_t chunk_ctr = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++tile) {
+        int mb, nb0, nbn;
+        decode(u, mb, nb0, nbn);
+        const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const int m = mb * 128 + row;
+        for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
+          const int n0 = nb0 * BLOCK_N + c * CH_ELEMS;
+          if (n0 >= p.N) break;  // uniform across the CTA
+          const uint32_t buf = chunk_ctr & 1;
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (threadIdx.x == 128) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          const uint32_t st_row = sEpi + buf * 16384 + row * 128;
+#pragma unroll
+          for (int h = 0; h < CH_ELEMS / 32; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + h * 32 + j;
+              float x = __uint_as_float(r[j]);
+              if (p.bias != nullptr && n < p.N) x += __ldg(p.bias + n);
+              v[j] = x;
+            }
+            if (p.residual != nullptr && m < p.M) {
+              const T* rp = reinterpret_cast<const T*>(p.residual) + (size_t)m * p.N + n0 + h * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + h * 32 + j < p.N) v[j] += (float)rp[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j];
+              if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+              if (p.act == ACT_RELU6) x = fminf(fmaxf(x, 0.f), 6.f);
+              v[j] = x;
+            }
+            if constexpr (sizeof(T) == 4) {
+              if (p.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+              }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {  // 8 x 16-byte units, XOR-swizzled like SWIZZLE_128B
+                const uint32_t a = st_row + (((uint32_t)q ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                             "f"(v[4 * q + 2]), "f"(v[4 * q + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+                  w[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                             "r"(w[3]));
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 128) {
+            tma_store_2d(&tmD, sEpi + buf * 16384, n0, mb * 128);
+            tma_store_commit();
+          }
+        }
+        // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      if (threadIdx.x == 128) tma_store_wait_all();
+    } else {
+      // ---------------------------------------------------------------- EPI_KNN
+      float* s_gn = reinterpret_cast<float*>(sEpi_gen);  // [2][BLOCK_N]
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int mb, nb0, nbn;
+        decode(u, mb, nb0, nbn);
+        float b1 = INFINITY, b2 = INFINITY;
+        int i1 = -1, i2 = -1;
+        for (int nb = nb0; nb < nb0 + nbn; ++nb, ++tile) {
+          const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+          float* gn = s_gn + as * BLOCK_N;
+          // stage the gallery norms of this n-block (previous user of this buffer finished two tiles ago; the
+          // barrier below also orders it against the other warps' reads of the other buffer)
+          for (int j = row; j < BLOCK_N; j += 128) {
+            const int n = nb * BLOCK_N + j;
+            gn[j] = (n < p.N) ? __ldg(p.gnorm + n) : INFINITY;
+          }
+          named_bar_sync(1, 128);
+          mbar_wait(tfull_bar(as), aphase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * 32, r);
+            tmem_ld_wait();
+            const int nbase = nb * BLOCK_N + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = fmaf(-2.f, __uint_as_float(r[j]), gn[c * 32 + j]);
+              if (s < b2) {
+                if (s < b1) {
+                  b2 = b1;
+                  i2 = i1;
+                  b1 = s;
+                  i1 = nbase + j;
+                } else {
+                  b2 = s;
+                  i2 = nbase + j;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        const int m = mb * 128 + row;
+        if (m < p.M) {
+          const int sp = nb0 / p.n_blocks_per_unit;
+          const size_t o = ((size_t)m * p.splits + sp) * 2;
+          p.part_score[o] = b1;
+          p.part_score[o + 1] = b2;
+          p.part_idx[o] = i1;
+          p.part_idx[o + 1] = i2;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace hfr

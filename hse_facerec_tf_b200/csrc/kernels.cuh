@@ -1,0 +1,601 @@
+// CUDA-core kernels of the hot path (everything that is not a dense contraction): input staging + stem convolution,
+// depthwise 3x3 (TMA halo staging), pooling, the dense heads, L2 normalisation and the 1-NN helper kernels.
+// All activations are NHWC.  T is the activation storage type: __nv_bfloat16 (bf16 mode) or float (tf32 / fp32 modes).
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace hfr {
+
+template <typename T>
+struct Vec16;  // 16-byte vector of T
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_RELU) x = fmaxf(x, 0.f);
+  if (act == ACT_RELU6) x = fminf(fmaxf(x, 0.f), 6.f);
+  return x;
+}
+template <typename T>
+__device__ __forceinline__ float finish(float x, int act, int rtf32) {
+  x = apply_act(x, act);
+  if (sizeof(T) == 4 && rtf32) x = round_tf32(x);
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stem: direct KHxKW convolution over a 3-channel image with the reference's pre-processing fused into the load
+// (facerec_test.py:96-110 / facial_analysis.py:102-107):  v[c] = in[flip ? 2-c : c] * scale - mean[c].
+// Zero padding is applied after pre-processing, as in the TF graph.  One thread = one output pixel x 32 channels.
+struct StemParams {
+  int B, H, W, Ho, Wo, KH, KW, stride, pad_t, pad_l, Cout;
+  int flip;
+  float scale, mean[3];
+  int act, round_tf32;
+};
+
+template <typename TIn, typename T>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, T* __restrict__ y,
+                                                        const StemParams p) {
+  extern __shared__ float s_w[];  // [KH*KW*3][32] slice of the weights for this channel group
+  const int cg = blockIdx.y;      // channel group of 32
+  const int ntap = p.KH * p.KW * 3;
+  for (int i = threadIdx.x; i < ntap * 32; i += blockDim.x) {
+    const int t = i >> 5, c = i & 31;
+    s_w[i] = w[(size_t)t * p.Cout + cg * 32 + c];
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)p.B * p.Ho * p.Wo;
+  if (pix >= npix) return;
+  const int ox = (int)(pix % p.Wo);
+  const int oy = (int)((pix / p.Wo) % p.Ho);
+  const int b = (int)(pix / ((long long)p.Wo * p.Ho));
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = bias ? bias[cg * 32 + c] : 0.f;
+  const TIn* xb = x + (size_t)b * p.H * p.W * 3;
+  for (int r = 0; r < p.KH; ++r) {
+    const int iy = oy * p.stride - p.pad_t + r;
+    if (iy < 0 || iy >= p.H) continue;
+    for (int s = 0; s < p.KW; ++s) {
+      const int ix = ox * p.stride - p.pad_l + s;
+      if (ix < 0 || ix >= p.W) continue;
+      const TIn* px = xb + ((size_t)iy * p.W + ix) * 3;
+      const float i0 = (float)px[0], i1 = (float)px[1], i2 = (float)px[2];
+      const float in3[3] = {p.flip ? i2 : i0, i1, p.flip ? i0 : i2};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = in3[c] * p.scale - p.mean[c];
+        const float4* wr = reinterpret_cast<const float4*>(s_w + ((r * p.KW + s) * 3 + c) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ww = wr[q];
+          acc[4 * q] = fmaf(v, ww.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  T* yo = y + (size_t)pix * p.Cout + cg * 32;
+  constexpr int VN = Vec16<T>::N;
+#pragma unroll
+  for (int q = 0; q < 32 / VN; ++q) {
+    float v[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) v[e] = finish<T>(acc[q * VN + e], p.act, p.round_tf32);
+    Vec16<T>::store(yo + q * VN, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 (+ per-channel scale folded into the taps, bias, ReLU6), stride 1 or 2, TF SAME/explicit padding.
+// HBM-bound: every input byte is fetched once by TMA into a shared-memory halo tile (out-of-range coordinates are
+// zero-filled by the TMA unit, which is exactly the zero padding), every output byte is written once as 16-byte
+// vectors.  CTA = 8x8 output pixels x (16 bytes * VL) channels; a thread owns one 16-byte channel vector of a
+// vertical strip of 4 outputs and slides the 3-row window through registers.
+struct DwParams {
+  int C, Ho, Wo, pad_t, pad_l, tiles_w, act, round_tf32;
+};
+
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                        const float* __restrict__ w,   // [9][C]
+                                                        const float* __restrict__ bias,  // [C]
+                                                        T* __restrict__ y, const DwParams p) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int TWI = 7 * STRIDE + 3;
+  constexpr int THI = 7 * STRIDE + 3;
+  extern __shared__ uint8_t dw_smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* dw_smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);  // TMA destination: 128-B aligned
+  const int VL = blockDim.x >> 4;  // 16-byte vector lanes per pixel (4 or 8)
+  const int cbe = VL * VN;         // channels per CTA
+  const int tile = blockIdx.x;
+  const int ox0 = (tile % p.tiles_w) * 8, oy0 = (tile / p.tiles_w) * 8;
+  const int c0 = blockIdx.y * cbe;
+  const int b = blockIdx.z;
+  const uint32_t sm = smem_u32(dw_smem);
+  const uint32_t sbar = smem_u32(&bar);
+  if (threadIdx.x == 0) {
+    mbar_init(sbar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(sbar, (uint32_t)(TWI * THI * cbe * sizeof(T)));
+    tma_load_4d(sm, &tmX, sbar, c0, ox0 * STRIDE - p.pad_l, oy0 * STRIDE - p.pad_t, b);
+  }
+  const int v = threadIdx.x % VL;
+  const int strip = threadIdx.x / VL;  // 0..15
+  const int lx = strip & 7;            // output column within the tile
+  const int ly0 = (strip >> 3) * 4;    // first output row of the strip
+  const int c = c0 + v * VN;
+  float wt[9][VN], bs[VN];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) wt[t][e] = __ldg(w + (size_t)t * p.C + c + e);
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) bs[e] = __ldg(bias + c + e);
+  __syncthreads();  // barrier init visible to all waiters
+  mbar_wait(sbar, 0);
+
+  float acc[4][VN];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
+  const T* tile_s = reinterpret_cast<const T*>(dw_smem);
+  constexpr int NROWS = 3 * STRIDE + 3;  // input rows touched by 4 vertically adjacent outputs
+#pragma unroll
+  for (int r = 0; r < NROWS; ++r) {
+    const int iy = ly0 * STRIDE + r;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = lx * STRIDE + s;
+      float xv[VN];
+      Vec16<T>::load(tile_s + ((size_t)(iy * TWI + ix) * VL + v) * VN, xv);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int kr = r - o * STRIDE;  // filter row this input row hits for output o
+        if (kr >= 0 && kr < 3) {
+#pragma unroll
+          for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wt[kr * 3 + s][e], acc[o][e]);
+        }
+      }
+    }
+  }
+  const int ox = ox0 + lx;
+  if (ox < p.Wo) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int oy = oy0 + ly0 + o;
+      if (oy < p.Ho) {
+        float ov[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
+        Vec16<T>::store(y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c, ov);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Max pooling (k x k, stride s) over NHWC, 16-byte channel vectors.  Out-of-range taps are skipped (TF SAME) unless
+// explicit_zero is set (TF Pad followed by a VALID MaxPool: the pad pixels are real zeros and take part in the max).
+struct PoolParams {
+  int B, H, W, C, Ho, Wo, k, stride, pad_t, pad_l, explicit_zero;
+};
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, const PoolParams p) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = p.C / VN;
+  const long long total = (long long)p.B * p.Ho * p.Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int ox = (int)(t % p.Wo);
+    t /= p.Wo;
+    const int oy = (int)(t % p.Ho);
+    const int b = (int)(t / p.Ho);
+    float m[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < p.k; ++r) {
+      const int iy = oy * p.stride - p.pad_t + r;
+      for (int s = 0; s < p.k; ++s) {
+        const int ix = ox * p.stride - p.pad_l + s;
+        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) {
+          if (p.explicit_zero) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) m[e] = fmaxf(m[e], 0.f);
+          }
+          continue;
+        }
+        float xv[VN];
+        Vec16<T>::load(x + (((size_t)b * p.H + iy) * p.W + ix) * p.C + v * VN, xv);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) m[e] = fmaxf(m[e], xv[e]);
+      }
+    }
+    Vec16<T>::store(y + (size_t)i * VN, m);
+  }
+}
+
+// Spatial subsampling y[b,oy,ox,:] = x[b,oy*s,ox*s,:] - the gather in front of a strided 1x1 convolution.
+template <typename T>
+__global__ void subsample_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho,
+                                 int Wo, int s) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = C / VN;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const uint4 val = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + oy * s) * W + ox * s) * C + v * VN);
+    *reinterpret_cast<uint4*>(y + (size_t)i * VN) = val;
+  }
+}
+
+// Global average pool [B, HW, C] (T) -> [B, C] fp32.  grid (B, C/(VN*32)); 32 channel-vector lanes x 8 pixel slices
+// per CTA, slices combined through shared memory.  Matches TF Mean(axis=[1,2]) / AvgPool(HxW, VALID).
+template <typename T>
+__global__ void __launch_bounds__(256) gap_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  constexpr int VN = Vec16<T>::N;
+  __shared__ float red[8][32][VN];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int cvec = blockIdx.y * 32 + lane;
+  const int b = blockIdx.x;
+  float acc[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+  if (cvec * VN < C) {
+    for (int px = slice; px < HW; px += 8) {
+      float xv[VN];
+      Vec16<T>::load(x + ((size_t)b * HW + px) * C + cvec * VN, xv);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] += xv[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) red[slice][lane][e] = acc[e];
+  __syncthreads();
+  if (slice == 0 && cvec * VN < C) {
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][lane][e];
+      y[(size_t)b * C + cvec * VN + e] = s * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense head: y[B,N] = act(x[B,K] * W[K,N] + bias), fp32.  act: 0 none, 1 relu, 3 sigmoid, 4 softmax (whole row in
+// one CTA).  CTA = 8 batch rows x up to 256 columns; x rows are staged in smem and broadcast.
+enum { FC_NONE = 0, FC_RELU = 1, FC_SIGMOID = 3, FC_SOFTMAX = 4 };
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                 const float* __restrict__ bias, float* __restrict__ y, int B, int K,
+                                                 int N, int act) {
+  extern __shared__ float s_fc[];  // [8][K] inputs, [8][256] logits, [8][2] softmax stats
+  float* sx = s_fc;
+  float* sl = s_fc + 8 * K;
+  const int b0 = blockIdx.x * 8;
+  const int n = blockIdx.y * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    sx[i] = (b0 + r < B) ? x[(size_t)(b0 + r) * K + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  if (n < N) {
+    for (int k = 0; k < K; ++k) {
+      const float ww = __ldg(w + (size_t)k * N + n);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = fmaf(sx[r * K + k], ww, acc[r]);
+    }
+    const float bb = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float v = acc[r] + bb;
+      if (act == FC_RELU) v = fmaxf(v, 0.f);
+      if (act == FC_SIGMOID) v = 1.f / (1.f + expf(-v));
+      acc[r] = v;
+    }
+  }
+  if (act == FC_SOFTMAX) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sl[r * 256 + threadIdx.x] = (n < N) ? acc[r] : -INFINITY;
+    __syncthreads();
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp r reduces row r
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sl[wrp * 256 + j]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) sum += expf(sl[wrp * 256 + j] - mx);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float* st = sl + 8 * 256;  // [8][2] (max, sum) per row
+    if (lane == 0) {
+      st[wrp * 2] = mx;
+      st[wrp * 2 + 1] = sum;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = expf(acc[r] - st[r * 2]) / st[r * 2 + 1];
+  }
+  if (n < N) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (b0 + r < B) y[(size_t)(b0 + r) * N + n] = acc[r];
+  }
+}
+
+// facial_analysis.py:113-124: indices = argsort(p)[::-1][:2] (ties -> higher index first), age = 1 + sum(i*p_i)/sum(p_i).
+__global__ void age_post_kernel(const float* __restrict__ probs, float* __restrict__ age, int B, int N) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float p1 = -INFINITY, p2 = -INFINITY;
+  int i1 = -1, i2 = -1;
+  auto push = [&](float v, int i) {
+    if (i < 0) return;
+    if (v > p1 || (v == p1 && i > i1)) {
+      p2 = p1; i2 = i1; p1 = v; i1 = i;
+    } else if (v > p2 || (v == p2 && i > i2)) {
+      p2 = v; i2 = i;
+    }
+  };
+  for (int j = lane; j < N; j += 32) push(probs[(size_t)row * N + j], j);
+  for (int o = 16; o; o >>= 1) {
+    const float q1 = __shfl_xor_sync(0xffffffffu, p1, o), q2 = __shfl_xor_sync(0xffffffffu, p2, o);
+    const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    push(q1, j1);
+    push(q2, j2);
+  }
+  if (lane == 0) {
+    const float s = p1 + p2;
+    age[row] = 1.f + ((float)i1 * (p1 / s) + (float)i2 * (p2 / s));
+  }
+}
+
+// sklearn.preprocessing.normalize(X, 'l2') (facerec_test.py:262,405): fp32 norms, zero rows stay zero.  Warp per row.
+__global__ void l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int d) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) s = fmaf(xr[j], xr[j], s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float nrm = sqrtf(s);
+  for (int j = lane; j < d; j += 32) y[row * d + j] = nrm == 0.f ? xr[j] : xr[j] / nrm;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM (precision mode 0): C = act(A[M,K] * B[N,K]^T + bias (+ residual)).  64x64 tile, 4x4 per thread.
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                    const float* __restrict__ bias, const float* __restrict__ res,
+                                                    float* __restrict__ C, int M, int N, int K, int act) {
+  __shared__ float sa[16][64 + 4], sb[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      sa[k][r] = (m0 + r < M && k0 + k < K) ? A[(size_t)(m0 + r) * K + k0 + k] : 0.f;
+      sb[k][r] = (n0 + r < N && k0 + k < K) ? Bm[(size_t)(n0 + r) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (res) v += res[(size_t)m * N + n];
+      C[(size_t)m * N + n] = apply_act(v, act);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 1-NN helpers.
+// rows fp32 -> bf16 copy (optional) + squared L2 norms in fp32.  Warp per row.
+__global__ void rows_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ nrm,
+                                 long long n, int d) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int j = lane * 4; j < d; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + j);
+    s = fmaf(v.x, v.x, s);
+    s = fmaf(v.y, v.y, s);
+    s = fmaf(v.z, v.z, s);
+    s = fmaf(v.w, v.w, s);
+    if (xb) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(xb + row * d + j) = o;
+    }
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && nrm) nrm[row] = s;
+}
+
+// Final selection: per query, merge the per-split top-2 candidates, keep the KEEP best approximate scores, then re-rank
+// those exactly - squared euclidean distance accumulated in fp64 from the fp32 originals (sklearn computes in fp64:
+// _argkmin.pyx / _middle_term_computer.pyx) - ties to the lowest gallery index.  Warp per query.
+template <int KEEP>
+__global__ void knn_finalize_kernel(const float* __restrict__ q, const float* __restrict__ g,
+                                    const float* __restrict__ part_score, const int* __restrict__ part_idx, int splits,
+                                    long long nq, int d, long long row_offset, float* __restrict__ best_dist,
+                                    long long* __restrict__ best_idx) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  const int ncand = splits * 2;
+  // each lane keeps its own KEEP best, then the warp extracts the global KEEP best one at a time
+  float ls[KEEP];
+  int li[KEEP];
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    ls[k] = INFINITY;
+    li[k] = -1;
+  }
+  for (int j = lane; j < ncand; j += 32) {
+    float s = part_score[row * ncand + j];
+    int i = part_idx[row * ncand + j];
+    if (i < 0) continue;
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      if (s < ls[k] || (s == ls[k] && i < li[k])) {
+        const float ts = ls[k];
+        const int ti = li[k];
+        ls[k] = s;
+        li[k] = i;
+        s = ts;
+        i = ti;
+      }
+    }
+  }
+  double bd = INFINITY;
+  int bi = -1;
+  for (int k = 0; k < KEEP; ++k) {
+    // warp-wide minimum of the lanes' current heads
+    float hs = ls[0];
+    int hi = li[0];
+    for (int o = 16; o; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, hs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, hi, o);
+      if (oi >= 0 && (hi < 0 || os < hs || (os == hs && oi < hi))) {
+        hs = os;
+        hi = oi;
+      }
+    }
+    if (hi < 0) break;
+    if (li[0] == hi) {  // pop it from the owning lane
+#pragma unroll
+      for (int t = 0; t + 1 < KEEP; ++t) {
+        ls[t] = ls[t + 1];
+        li[t] = li[t + 1];
+      }
+      ls[KEEP - 1] = INFINITY;
+      li[KEEP - 1] = -1;
+    }
+    const float* qr = q + row * d;
+    const float* gr = g + (long long)hi * d;
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) {
+      const double df = (double)qr[j] - (double)gr[j];
+      acc = fma(df, df, acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (acc < bd || (acc == bd && hi < bi)) {
+      bd = acc;
+      bi = hi;
+    }
+  }
+  if (lane == 0) {
+    best_dist[row] = (float)bd;
+    best_idx[row] = bi < 0 ? -1 : row_offset + bi;
+  }
+}
+
+// Merge P per-shard results (gathered as [P][nq]) into the global best: smallest distance, ties to the lowest index.
+__global__ void knn_merge_kernel(const float* __restrict__ dist_all, const long long* __restrict__ idx_all, int parts,
+                                 long long nq, float* __restrict__ best_dist, long long* __restrict__ best_idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float bd = INFINITY;
+  long long bi = -1;
+  for (int p = 0; p < parts; ++p) {
+    const float dd = dist_all[(size_t)p * nq + i];
+    const long long ii = idx_all[(size_t)p * nq + i];
+    if (ii < 0) continue;
+    if (bi < 0 || dd < bd || (dd == bd && ii < bi)) {
+      bd = dd;
+      bi = ii;
+    }
+  }
+  best_dist[i] = bd;
+  best_idx[i] = bi;
+}
+
+template <typename T>
+__global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, long long n, int rtf32) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (sizeof(T) == 4 && rtf32) v = round_tf32(v);
+    y[i] = (T)v;
+  }
+}
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = (float)x[i];
+}
+
+}  // namespace hfr

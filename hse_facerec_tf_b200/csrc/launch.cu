@@ -1,0 +1,391 @@
+// Kernel launchers: tensor-map construction (driver entry points resolved at run time, no libcuda link dependency),
+// tile-shape selection and grid sizing for the sm_100a kernels in kernels.cuh / gemm_tc.cuh.
+#include "launch.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+#include "kernels.cuh"
+
+namespace hfr {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_count() { return g_launches.load(); }
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw Error(-6, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define HFR_LAUNCH_CHECK(name)                    \
+  do {                                            \
+    g_launches.fetch_add(1);                      \
+    cuda_check(cudaGetLastError(), "launch " name); \
+  } while (0)
+
+int device_sm_count(int device) {
+  static std::mutex mu;
+  static int cache[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64) throw Error(-1, "bad device index");
+  if (cache[device] == 0) {
+    cudaDeviceProp p;
+    cuda_check(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties");
+    if (p.major != 10) throw Error(-6, "device " + std::to_string(device) + " is sm_" + std::to_string(p.major) +
+                                           std::to_string(p.minor) + "; this library contains sm_100a code only");
+    cache[device] = p.multiProcessorCount;
+  }
+  return cache[device];
+}
+
+void use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) throw Error(-6, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= n) throw Error(-1, "device index out of range");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  device_sm_count(device);
+}
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void* driver_fn(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cuda_check(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q), name);
+  if (q != cudaDriverEntryPointSuccess || !fn) throw Error(-6, std::string("driver entry point not found: ") + name);
+  return fn;
+}
+
+static CUtensorMapDataType tmap_dtype(int prec) {
+  return prec == PREC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+// rank-N tiled map; dims/strides innermost first; strides in bytes for dims 1..rank-1
+static CUtensorMap make_tiled(const void* ptr, int prec, int rank, const uint64_t* dims, const uint64_t* strides,
+                              const uint32_t* box, CUtensorMapSwizzle swz) {
+  static PFN_encodeTiled enc = (PFN_encodeTiled)driver_fn("cuTensorMapEncodeTiled");
+  CUtensorMap m;
+  uint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&m, tmap_dtype(prec), (cuuint32_t)rank, const_cast<void*>(ptr), (const cuuint64_t*)dims,
+                   (const cuuint64_t*)strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-6, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
+// 2-D row-major [rows, cols] matrix, box = {128 bytes of columns, box_rows}, SWIZZLE_128B
+static CUtensorMap make_tmap_2d(const void* ptr, int prec, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {cols * elt_size(prec)};
+  const uint32_t box[2] = {(uint32_t)(128 / elt_size(prec)), box_rows};
+  return make_tiled(ptr, prec, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// ---------------------------------------------------------------------------------------------- stem
+template <typename TIn, typename T>
+static void launch_stem_t(const StemArgs& a, cudaStream_t s) {
+  StemParams p;
+  p.B = a.B; p.H = a.H; p.W = a.W; p.Ho = a.Ho; p.Wo = a.Wo; p.KH = a.kh; p.KW = a.kw; p.stride = a.stride;
+  p.pad_t = a.pad_t; p.pad_l = a.pad_l; p.Cout = a.cout; p.flip = a.flip; p.scale = a.scale;
+  for (int i = 0; i < 3; ++i) p.mean[i] = a.mean[i];
+  p.act = a.act; p.round_tf32 = a.round_tf32;
+  const long long npix = (long long)a.B * a.Ho * a.Wo;
+  dim3 grid((unsigned)((npix + 127) / 128), (unsigned)(a.cout / 32));
+  const size_t smem = (size_t)a.kh * a.kw * 3 * 32 * sizeof(float);
+  stem_conv_kernel<TIn, T><<<grid, 128, smem, s>>>((const TIn*)a.x, a.w, a.bias, (T*)a.y, p);
+  HFR_LAUNCH_CHECK("stem_conv");
+}
+void launch_stem(const StemArgs& a, int prec, cudaStream_t s) {
+  if (a.cout % 32) throw Error(-1, "stem: cout must be a multiple of 32");
+  if ((size_t)a.kh * a.kw * 3 * 32 * 4 > 48 * 1024) throw Error(-5, "stem: kernel window too large");
+  if (prec == PREC_BF16) {
+    if (a.in_u8) launch_stem_t<uint8_t, __nv_bfloat16>(a, s); else launch_stem_t<float, __nv_bfloat16>(a, s);
+  } else {
+    if (a.in_u8) launch_stem_t<uint8_t, float>(a, s); else launch_stem_t<float, float>(a, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- depthwise
+template <typename T, int STRIDE>
+static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
+  constexpr int VN = Vec16<T>::N;
+  const int es = (int)sizeof(T);
+  int VL = (a.C * es) / 16;
+  if (VL > 8) VL = 8;
+  if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
+  const int cbe = VL * VN;
+  if (a.C % cbe) throw Error(-1, "depthwise: channels must be a multiple of the channel block");
+  constexpr int TI = 7 * STRIDE + 3;
+  const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t strides[3] = {(uint64_t)a.C * es, (uint64_t)a.W * a.C * es, (uint64_t)a.H * a.W * a.C * es};
+  const uint32_t box[4] = {(uint32_t)cbe, (uint32_t)TI, (uint32_t)TI, 1};
+  CUtensorMap tm = make_tiled(a.x, prec, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  DwParams p;
+  p.C = a.C; p.Ho = a.Ho; p.Wo = a.Wo; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
+  p.tiles_w = (a.Wo + 7) / 8;
+  p.act = a.act; p.round_tf32 = a.round_tf32;
+  const int tiles_h = (a.Ho + 7) / 8;
+  dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(a.C / cbe), (unsigned)a.B);
+  const size_t smem = (size_t)TI * TI * cbe * es + 128;
+  dwconv3x3_kernel<T, STRIDE><<<grid, 16 * VL, smem, s>>>(tm, a.w, a.bias, (T*)a.y, p);
+  HFR_LAUNCH_CHECK("dwconv3x3");
+}
+void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
+  if (a.B > 65535) throw Error(-1, "depthwise: batch too large for one launch");
+  if (a.stride == 1) {
+    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 1>(a, prec, s); else launch_dw_t<float, 1>(a, prec, s);
+  } else if (a.stride == 2) {
+    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 2>(a, prec, s); else launch_dw_t<float, 2>(a, prec, s);
+  } else {
+    throw Error(-5, "depthwise: stride must be 1 or 2");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GEMM (tcgen05)
+template <typename T, int BLOCK_N, int EPI, int AMODE>
+static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const GemmParams& p,
+                             int device, cudaStream_t s) {
+  using SM = GemmSmem<BLOCK_N, EPI>;
+  auto kern = gemm_tc_kernel<T, BLOCK_N, EPI, AMODE>;
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal),
+               "cudaFuncSetAttribute(gemm smem)");
+    configured[device].store(true);
+  }
+  int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
+  if (grid < 1) return;
+  kern<<<grid, 256, SM::kTotal, s>>>(tA, tB, tD, p);
+  HFR_LAUNCH_CHECK("gemm_tc");
+}
+
+static int pick_block_n(int64_t M, int N, int sms) {
+  const int64_t mb = (M + 127) / 128;
+  const int cands[3] = {256, 128, 64};
+  for (int c : cands) {
+    if (c > N && c != 64) continue;
+    if (N % c != 0 && c != 64) continue;
+    if (mb * ((N + c - 1) / c) >= sms) return c;
+  }
+  return 64;
+}
+
+template <typename T, int AMODE>
+static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, GemmParams p, int64_t M, int N, int K,
+                              int prec, int device, cudaStream_t s) {
+  const int bn = pick_block_n(M, N, device_sm_count(device));
+  CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
+  CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
+  p.num_m_blocks = (int)((M + 127) / 128);
+  p.num_n_blocks = (N + bn - 1) / bn;
+  p.n_blocks_per_unit = 1;
+  p.num_units = p.num_m_blocks * p.num_n_blocks;
+  if (bn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
+  else if (bn == 128) launch_gemm_inst<T, 128, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
+  else launch_gemm_inst<T, 64, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
+}
+
+void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
+  if (a.M <= 0) return;
+  if (prec == PREC_FP32) {
+    dim3 grid((unsigned)((a.N + 63) / 64), (unsigned)((a.M + 63) / 64));
+    sgemm_kernel<<<grid, 256, 0, s>>>((const float*)a.a, (const float*)a.b, a.bias, (const float*)a.residual,
+                                       (float*)a.y, (int)a.M, a.N, a.K, a.act);
+    HFR_LAUNCH_CHECK("sgemm");
+    return;
+  }
+  const int es = (int)elt_size(prec);
+  if ((a.K * es) % 16 || (a.N * es) % 16) throw Error(-1, "gemm: K and N rows must be multiples of 16 bytes");
+  if (a.M >= (1ll << 31)) throw Error(-1, "gemm: M too large");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)a.M; p.N = a.N; p.K = a.K;
+  p.bias = a.bias; p.residual = a.residual; p.act = a.act; p.round_tf32 = a.round_tf32;
+  CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
+  if (prec == PREC_BF16) launch_gemm_store<__nv_bfloat16, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
+  else launch_gemm_store<float, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
+}
+
+// ---------------------------------------------------------------------------------------------- implicit-GEMM conv
+void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s) {
+  if (prec == PREC_FP32) throw Error(-5, "KxK convolutions run on the tensor-core path only (tf32 / bf16 precision)");
+  static PFN_encodeIm2col enc = (PFN_encodeIm2col)driver_fn("cuTensorMapEncodeIm2col");
+  const int es = (int)elt_size(prec);
+  const int bk = 128 / es;
+  if (a.cin % bk) throw Error(-1, "conv: input channels must be a multiple of the 128-byte K block");
+  if (a.kh != a.kw) throw Error(-5, "conv: square kernels only");
+  const int64_t M = (int64_t)a.B * a.Ho * a.Wo;
+  const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t strides[3] = {(uint64_t)a.cin * es, (uint64_t)a.W * a.cin * es, (uint64_t)a.H * a.W * a.cin * es};
+  // bounding box of filter-window origins (fprop): lower = -pad_before, upper = pad_after - (k-1)*dil, with the
+  // trailing pad chosen so that exactly Ho x Wo window positions exist at the traversal stride
+  const int span = (a.kw - 1) * a.dil;
+  const int pad_r = (a.Wo - 1) * a.stride + span + 1 - a.W - a.pad_l;
+  const int pad_b = (a.Ho - 1) * a.stride + span + 1 - a.H - a.pad_t;
+  int lower[2] = {-a.pad_l, -a.pad_t};
+  int upper[2] = {pad_r - span, pad_b - span};
+  uint32_t estr[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
+  CUtensorMap tA;
+  CUresult r = enc(&tA, tmap_dtype(prec), 4, const_cast<void*>(a.x), (const cuuint64_t*)dims,
+                   (const cuuint64_t*)strides, lower, upper, (cuuint32_t)bk, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-6, "cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = a.cout; p.K = a.kh * a.kw * a.cin;
+  p.bias = a.bias; p.residual = a.residual; p.act = a.act; p.round_tf32 = a.round_tf32;
+  p.conv_kw = a.kw; p.conv_cblocks = a.cin / bk; p.conv_wo = a.Wo; p.conv_ho = a.Ho;
+  p.conv_stride = a.stride; p.conv_pad_w = a.pad_l; p.conv_pad_h = a.pad_t; p.conv_dil = a.dil;
+  if (prec == PREC_BF16)
+    launch_gemm_store<__nv_bfloat16, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s);
+  else
+    launch_gemm_store<float, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s);
+}
+
+// ---------------------------------------------------------------------------------------------- simple kernels
+static unsigned grid_for(long long total, int threads, long long cap = 148LL * 32) {
+  long long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s) {
+  PoolParams p;
+  p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.Ho = a.Ho; p.Wo = a.Wo; p.k = a.k; p.stride = a.stride;
+  p.pad_t = a.pad_t; p.pad_l = a.pad_l; p.explicit_zero = a.explicit_zero;
+  const int vn = prec == PREC_BF16 ? 8 : 4;
+  if (a.C % vn) throw Error(-1, "maxpool: channels must be a multiple of the 16-byte vector");
+  const long long total = (long long)a.B * a.Ho * a.Wo * (a.C / vn);
+  if (prec == PREC_BF16)
+    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, p);
+  else
+    maxpool_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)a.x, (float*)a.y, p);
+  HFR_LAUNCH_CHECK("maxpool");
+}
+
+void launch_subsample(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, int stride, int prec,
+                      cudaStream_t s) {
+  const int vn = prec == PREC_BF16 ? 8 : 4;
+  const long long total = (long long)B * Ho * Wo * (C / vn);
+  if (prec == PREC_BF16)
+    subsample_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B,
+                                                                          H, W, C, Ho, Wo, stride);
+  else
+    subsample_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)x, (float*)y, B, H, W, C, Ho, Wo, stride);
+  HFR_LAUNCH_CHECK("subsample");
+}
+
+void launch_gap(const void* x, float* y, int B, int HW, int C, int prec, cudaStream_t s) {
+  const int vn = prec == PREC_BF16 ? 8 : 4;
+  dim3 grid((unsigned)B, (unsigned)((C / vn + 31) / 32));
+  if (prec == PREC_BF16) gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, y, HW, C);
+  else gap_kernel<float><<<grid, 256, 0, s>>>((const float*)x, y, HW, C);
+  HFR_LAUNCH_CHECK("gap");
+}
+
+void launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
+               cudaStream_t s) {
+  if (act == FC_SOFTMAX && N > 256) throw Error(-5, "dense+softmax: at most 256 classes");
+  const size_t smem = ((size_t)8 * K + 8 * 256 + 16) * sizeof(float);
+  if (smem > 200 * 1024) throw Error(-5, "dense: input dimension too large");
+  cuda_check(cudaFuncSetAttribute(fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+             "cudaFuncSetAttribute(fc smem)");
+  dim3 grid((unsigned)((B + 7) / 8), (unsigned)((N + 255) / 256));
+  fc_kernel<<<grid, 256, smem, s>>>(x, w, bias, y, B, K, N, act);
+  HFR_LAUNCH_CHECK("fc");
+}
+
+void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {
+  age_post_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(probs, age, B, N);
+  HFR_LAUNCH_CHECK("age_post");
+}
+
+void launch_l2norm(const float* x, float* y, int64_t n, int d, cudaStream_t s) {
+  if (n <= 0) return;
+  l2norm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(x, y, (long long)n, d);
+  HFR_LAUNCH_CHECK("l2norm");
+}
+
+void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream_t s) {
+  if (prec == PREC_BF16) {
+    cast_to_f32_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>((const __nv_bfloat16*)x, y, (long long)n);
+    HFR_LAUNCH_CHECK("cast_to_f32");
+  } else {
+    cuda_check(cudaMemcpyAsync(y, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
+  }
+}
+void launch_cast_from_f32(const float* x, void* y, int64_t n, int prec, cudaStream_t s) {
+  if (prec == PREC_BF16)
+    cast_f32_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, (long long)n, 0);
+  else
+    cast_f32_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(x, (float*)y, (long long)n, prec == PREC_TF32);
+  HFR_LAUNCH_CHECK("cast_from_f32");
+}
+
+// ---------------------------------------------------------------------------------------------- 1-NN
+void launch_rows_prep(const float* x, void* xb, float* norms, int64_t n, int d, cudaStream_t s) {
+  if (n <= 0) return;
+  if (d % 4) throw Error(-1, "1-NN: dimension must be a multiple of 4");
+  rows_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(x, (__nv_bfloat16*)xb, norms, (long long)n, d);
+  HFR_LAUNCH_CHECK("rows_prep");
+}
+
+void knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit) {
+  const int64_t nb = (n + 255) / 256;
+  const int64_t mb = (nq + 127) / 128;
+  int64_t sp = (1184 + mb - 1) / mb;           // enough units to balance 148 persistent CTAs
+  const int64_t sp_min = (nb + 63) / 64;       // at most 64 n-blocks (16384 gallery rows, L2-sized) per unit
+  if (sp < sp_min) sp = sp_min;
+  if (sp > nb) sp = nb;
+  if (sp < 1) sp = 1;
+  const int64_t per = (nb + sp - 1) / sp;
+  *n_blocks_per_unit = (int)per;
+  *splits = (int)((nb + per - 1) / per);
+}
+
+void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s) {
+  if (prec != PREC_BF16 && prec != PREC_TF32) throw Error(-1, "1-NN: precision must be tf32 or bf16");
+  const int es = (int)elt_size(prec);
+  if ((a.d * es) % 16) throw Error(-1, "1-NN: rows must be multiples of 16 bytes");
+  if (a.nq >= (1ll << 31) || a.n >= (1ll << 31)) throw Error(-1, "1-NN: shard too large for 32-bit indices");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)a.nq; p.N = (int)a.n; p.K = a.d;
+  p.num_m_blocks = (int)((a.nq + 127) / 128);
+  p.num_n_blocks = (int)((a.n + 255) / 256);
+  p.n_blocks_per_unit = a.n_blocks_per_unit;
+  p.splits = a.splits;
+  p.num_units = p.num_m_blocks * a.splits;
+  p.gnorm = a.gnorm; p.part_score = a.part_score; p.part_idx = a.part_idx;
+  CUtensorMap tA = make_tmap_2d(a.q, prec, (uint64_t)a.nq, (uint64_t)a.d, 128);
+  CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 256);
+  if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, p, device, s);
+  else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, p, device, s);
+}
+
+void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
+                         int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s) {
+  if (nq <= 0) return;
+  knn_finalize_kernel<4><<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(q, g, part_score, part_idx, splits, (long long)nq, d,
+                                                                  (long long)row_offset, best_dist,
+                                                                  (long long*)best_idx);
+  HFR_LAUNCH_CHECK("knn_finalize");
+}
+
+void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
+                      int64_t* best_idx, cudaStream_t s) {
+  if (nq <= 0) return;
+  knn_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(dist_all, (const long long*)idx_all, parts,
+                                                                 (long long)nq, best_dist, (long long*)best_idx);
+  HFR_LAUNCH_CHECK("knn_merge");
+}
+
+}  // namespace hfr

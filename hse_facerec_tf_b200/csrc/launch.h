@@ -1,0 +1,104 @@
+// Host-callable launchers for every kernel of the hot path (implemented in launch.cu).  All functions enqueue work on
+// `stream` and throw hfr::Error on failure; none of them synchronises.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace hfr {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void cuda_check(cudaError_t e, const char* what);
+
+enum { PREC_FP32 = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
+inline size_t elt_size(int prec) { return prec == PREC_BF16 ? 2 : 4; }
+
+int device_sm_count(int device);
+void use_device(int device);  // cudaSetDevice + sm_100 check
+int64_t launch_count();
+
+struct StemArgs {
+  const void* x;  // [B,H,W,3] u8 or f32
+  int in_u8;
+  const float* w;     // [kh][kw][3][cout]
+  const float* bias;  // [cout] or null
+  void* y;            // [B,Ho,Wo,cout] of T
+  int B, H, W, Ho, Wo, kh, kw, stride, pad_t, pad_l, cout;
+  int flip;
+  float scale, mean[3];
+  int act, round_tf32;
+};
+void launch_stem(const StemArgs& a, int prec, cudaStream_t s);
+
+struct DwArgs {
+  const void* x;      // [B,H,W,C] of T
+  const float* w;     // [9][C]
+  const float* bias;  // [C]
+  void* y;            // [B,Ho,Wo,C]
+  int B, H, W, C, Ho, Wo, stride, pad_t, pad_l, act, round_tf32;
+};
+void launch_dw(const DwArgs& a, int prec, cudaStream_t s);
+
+struct GemmArgs {
+  const void* a;         // [M,K] of T (row-major, K contiguous)
+  const void* b;         // [N,K] of T
+  const float* bias;     // [N] or null
+  const void* residual;  // [M,N] of T or null
+  void* y;               // [M,N] of T
+  int64_t M;
+  int N, K;
+  int act, round_tf32;
+};
+void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s);
+
+struct ConvArgs {  // KxK convolution as implicit GEMM (NHWC), weights [cout][kh*kw][cin]
+  const void* x;
+  const void* w;
+  const float* bias;
+  const void* residual;
+  void* y;
+  int B, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad_t, pad_l, dil;
+  int act, round_tf32;
+};
+void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s);
+
+struct PoolArgs {
+  const void* x;
+  void* y;
+  int B, H, W, C, Ho, Wo, k, stride, pad_t, pad_l, explicit_zero;
+};
+void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s);
+void launch_subsample(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, int stride, int prec,
+                      cudaStream_t s);
+void launch_gap(const void* x, float* y, int B, int HW, int C, int prec, cudaStream_t s);
+// act: 0 none, 1 relu, 3 sigmoid, 4 softmax
+void launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, cudaStream_t s);
+void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s);
+void launch_l2norm(const float* x, float* y, int64_t n, int d, cudaStream_t s);
+void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream_t s);
+void launch_cast_from_f32(const float* x, void* y, int64_t n, int prec, cudaStream_t s);
+
+// 1-NN
+void launch_rows_prep(const float* x, void* x_bf16_or_null, float* norms_or_null, int64_t n, int d, cudaStream_t s);
+struct KnnGemmArgs {
+  const void* q;  // [nq, d] of T
+  const void* g;  // [n, d] of T
+  const float* gnorm;
+  float* part_score;  // [nq][splits][2]
+  int* part_idx;
+  int64_t nq, n;
+  int d, splits, n_blocks_per_unit;
+};
+void knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
+void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s);
+void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
+                         int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s);
+void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
+                      int64_t* best_idx, cudaStream_t s);
+
+}  // namespace hfr

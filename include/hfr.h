@@ -1,0 +1,136 @@
+/* hfr.h - C ABI of libhfr.so: the B200-native replacement for the numeric back ends under the hot path of
+ * av-savchenko/HSE_FaceRec_tf (TensorFlow `sess.run`, Keras `model.predict`, scikit-learn 1-NN).
+ *
+ * The reference has no FFI of its own (it is Python calling TF/Keras/sklearn); each entry point below names the
+ * reference call site it stands in for (paths relative to the reference repository).  Plain pointers and sizes only;
+ * device pointers are CUDA device memory on the handle's device, `stream` is a cudaStream_t passed as void*.
+ *
+ * Error convention: every function returns 0 on success or a negative hfr_status; the message is available from
+ * hfr_last_error() (thread-local).  There is NO CPU fallback: compute entry points fail with HFR_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef HFR_H_
+#define HFR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hfr_model hfr_model;
+typedef struct hfr_knn hfr_knn;
+
+enum hfr_status {
+  HFR_OK = 0,
+  HFR_ERR_INVALID = -1,     /* bad argument (ValueError in the Python layer)                         */
+  HFR_ERR_IO = -2,          /* file missing / unreadable                                             */
+  HFR_ERR_FORMAT = -3,      /* not a GraphDef / HDF5 file, or malformed                              */
+  HFR_ERR_NOT_FOUND = -4,   /* tensor name not in graph (KeyError from graph.get_tensor_by_name)     */
+  HFR_ERR_UNSUPPORTED = -5, /* op / pattern outside the hot path                                     */
+  HFR_ERR_CUDA = -6,        /* CUDA runtime / driver failure, or no usable GPU                       */
+  HFR_ERR_STATE = -7        /* call order (e.g. query before set_gallery)                            */
+};
+
+enum hfr_precision {
+  HFR_FP32 = 0, /* fp32 storage, fp32 CUDA-core GEMMs (exact-parity mode)        */
+  HFR_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32 GEMMs, fp32 accumulate       */
+  HFR_BF16 = 2  /* bf16 storage, tcgen05 kind::f16 (bf16) GEMMs, fp32 accumulate */
+};
+
+enum hfr_input_dtype {
+  HFR_IN_F32 = 0, /* float32 NHWC, already pre-processed: what the reference feeds the placeholder               */
+  HFR_IN_U8 = 1   /* uint8 NHWC RGB crops; pre-processing (flags below) is fused into the first kernel           */
+};
+
+/* hfr_model_forward flags.  Pre-processing of facerec_test.py:96-110 / facial_analysis.py:102-107, for HFR_IN_U8. */
+#define HFR_FLAG_BGR 0x1            /* convert2BGR: reverse channel order                                */
+#define HFR_FLAG_MEAN_IMAGENET 0x2  /* subtract (103.939, 116.779, 123.68)   (imageNetUtilsMean=True)     */
+#define HFR_FLAG_MEAN_VGGFACE2 0x4  /* subtract (91.4953, 103.8827, 131.0912) (imageNetUtilsMean=False)   */
+#define HFR_FLAG_SCALE_PM1 0x8      /* x / 127.5 - 1                          (convert2BGR=False)         */
+#define HFR_FLAG_L2NORM 0x10        /* L2-normalise output 0 (sklearn.preprocessing.normalize, facerec_test.py:405) */
+#define HFR_FLAG_CUDA_GRAPH 0x20    /* replay the step from a captured CUDA graph (stream must not be the legacy stream) */
+
+const char* hfr_last_error(void);
+int hfr_version(void);
+/* Number of kernels this library has launched in this process (all handles); for `gpu_launches` accounting. */
+int64_t hfr_launch_count(void);
+
+/* ---- model: load + compile -------------------------------------------------------------------------------------
+ * Replaces load_graph + TensorFlowInference.__init__ (facerec_test.py:41-78), FacialImageProcessing.load_graph_def /
+ * load_age_gender (facial_analysis.py:83-92,319-325) and Keras load_weights('models/vgg2_mobilenet.h5')
+ * (facerec_test.py:326-334).  `path` is a frozen GraphDef (.pb) or a Keras HDF5 file (.h5, MobileNet-v1 layer names).
+ * `output_names_csv`: comma-separated tensor names, e.g. "age_pred/Softmax:0,gender_pred/Sigmoid:0,global_pooling/Mean:0".
+ * `phase_name` (nullable): learning-phase placeholder fed with `phase_value` (learning_phase_tensor /
+ * additional_input_value).  `input_hw`: 0 = the placeholder's static size; otherwise run the fully convolutional
+ * body at this size.  `device` < 0 parses and compiles on the host only (no CUDA needed): the handle then supports
+ * hfr_model_info / hfr_model_plan_json but not forward. */
+int hfr_model_load(const char* path, const char* input_name, const char* output_names_csv, const char* phase_name,
+                   float phase_value, int input_hw, int device, int precision, hfr_model** out);
+int hfr_model_info(const hfr_model* m, int* in_h, int* in_w, int* in_c, int* n_outputs, int* out_dims /*[n_outputs]*/);
+/* Fused layer plan as JSON (for tests / inspection).  Returns the length needed (incl. NUL) if buf is too small. */
+int64_t hfr_model_plan_json(const hfr_model* m, char* buf, int64_t buf_len);
+
+/* Folded fp32 weights / bias of plan layer `layer` as the compiler produced them (layouts: see "w" in the plan JSON
+ * kinds - stem [kh][kw][3][cout], dw [9][c], pw/conv [cout][kh*kw][cin], fc [k][n]).  Returns the weight element
+ * count; copies only when the capacities suffice.  Host-side, for checking the graph compiler without a GPU. */
+int64_t hfr_model_layer_weights(const hfr_model* m, int layer, float* w, int64_t w_cap, float* bias, int64_t b_cap);
+
+/* Replaces sess.run(outputs, {input: x}) (facerec_test.py:120, facial_analysis.py:109) on a whole batch.
+ * x: device pointer, NHWC [batch, H, W, 3] of `in_dtype`.  outs[i]: device pointer to float32 [batch, out_dims[i]]. */
+int hfr_model_forward(hfr_model* m, const void* x, int in_dtype, int batch, int flags, void* const* outs, void* stream);
+/* Same call with HOST buffers (numpy arrays in, numpy arrays out - the reference's calling convention): copies the
+ * batch host->device, runs, copies the outputs device->host and synchronises the stream. */
+int hfr_model_forward_host(hfr_model* m, const void* x_host, int in_dtype, int batch, int flags, void* const* outs_host,
+                           void* stream);
+/* Debug: give every activation its own buffer (no arena reuse) so hfr_model_debug_layer can read any of them. */
+int hfr_model_set_keep_activations(hfr_model* m, int keep);
+/* Intermediate activation of layer `layer_index` (plan order) from the last forward, converted to float32 NHWC on the
+ * device; for layer-by-layer parity checks.  Returns the element count per image, or a negative status. */
+int64_t hfr_model_debug_layer(hfr_model* m, int layer_index, int batch, float* dst, void* stream);
+void hfr_model_free(hfr_model* m);
+
+/* age = 1 + sum_{i in top2} i * p_i / sum_{top2} p   (facial_analysis.py:113-124); age_probs [batch, n] float32. */
+int hfr_age_gender_post(const float* age_probs, int batch, int n, float* age_out, int device, void* stream);
+/* sklearn.preprocessing.normalize(X, norm='l2') (facerec_test.py:262,265,405); in-place allowed (y == x). */
+int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, void* stream);
+
+/* ---- 1-NN identification ------------------------------------------------------------------------------------------
+ * Replaces KNeighborsClassifier(n_neighbors=1, p=2).fit / .kneighbors (facerec_test.py:272,284-285,422) - the euclidean
+ * ArgKmin reduction; label lookup stays with the caller.  A handle owns one gallery shard. */
+int hfr_knn_create(int device, int dim, int precision /* HFR_TF32 or HFR_BF16 */, hfr_knn** out);
+/* gallery: device float32 [n_local, dim], must stay alive and unchanged while the handle uses it (it is re-read for
+ * the exact re-ranking).  global_row_offset: index of the shard's first row in the full gallery. */
+int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64_t global_row_offset, void* stream);
+/* queries: device float32 [nq, dim] -> best_dist2 float32 [nq] (squared euclidean), best_idx int64 [nq] (global). */
+int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist2, int64_t* best_idx, void* stream);
+/* Host-buffer variant of set_gallery+query for the end-to-end path (copies in, runs, copies out, synchronises). */
+int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host, int64_t* best_idx_host,
+                       void* stream);
+/* Merge per-shard results gathered as [n_parts, nq] (e.g. by an NCCL all-gather): min distance, ties -> lowest index. */
+int hfr_knn_merge(const float* dist_all, const int64_t* idx_all, int n_parts, int64_t nq, float* best_dist2,
+                  int64_t* best_idx, int device, void* stream);
+void hfr_knn_free(hfr_knn* k);
+
+/* ---- single operators (kernel-level parity tests and profiling) ---------------------------------------------------
+ * dtype: HFR_FP32/HFR_TF32 -> float32 tensors, HFR_BF16 -> bfloat16 tensors.  act: 0 none, 1 relu, 2 relu6. */
+int hfr_op_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int batch, int h, int w, int c,
+                     int stride, int pad_t, int pad_l, int ho, int wo, int act, int dtype, int device, void* stream);
+/* y[M,N] = act(a[M,K] * b[N,K]^T + bias (+ residual[M,N])) */
+int hfr_op_gemm_bias_act(const void* a, const void* b, const float* bias, const void* residual, void* y, int64_t m,
+                         int n, int k, int act, int dtype, int device, void* stream);
+int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* bias, void* y, int batch, int h, int w_,
+                     int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act,
+                     int dtype, int device, void* stream);
+
+/* KxK convolution (square kernel, implicit GEMM on tensor cores; tf32/bf16 only). w: [cout][kh*kw][cin] of dtype. */
+int hfr_op_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int batch, int h,
+                  int w_, int cin, int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int act,
+                  int dtype, int device, void* stream);
+int hfr_op_maxpool(const void* x, void* y, int batch, int h, int w, int c, int k, int stride, int pad_t, int pad_l,
+                   int ho, int wo, int explicit_zero, int dtype, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFR_H_ */

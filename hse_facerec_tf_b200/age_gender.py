@@ -1,0 +1,65 @@
+"""Drop-in for the age/gender path of age_gender_identity/facial_analysis.py.
+
+  FacialImageProcessing.load_age_gender -> age_gender_fun   facial_analysis.py:83-130
+  FacialImageProcessing.is_male                             facial_analysis.py:76-81
+
+Detection (MTCNN / LBP cascade, facial_analysis.py:210-604) is upstream of the hot path and is not part of this class.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .model import HfrModel, _stream_ptr
+
+AGE_GENDER_OUTPUTS = ["age_pred/Softmax:0", "gender_pred/Sigmoid:0", "global_pooling/Mean:0"]
+
+
+class FacialImageProcessing:
+    def __init__(self, model_file, print_stat=False, device="cuda:0", precision="bf16"):
+        self.print_stat = print_stat
+        self.model = HfrModel(model_file, "input_1:0", AGE_GENDER_OUTPUTS, device=device, precision=precision)
+        self.age_gender_fun = self.load_age_gender()
+
+    def close(self):
+        self.model.close()
+
+    @staticmethod
+    def is_male(gender_preds):
+        return gender_preds >= 0.6
+
+    # -- batched -------------------------------------------------------------------------------------
+    def age_gender_batch(self, x, graph=False):
+        """x: [B,H,W,3] RGB uint8 crops already resized to the network size (CUDA tensor or numpy).
+        Returns (age [B], gender [B,1], feat [B,1024], age_probs [B,100]); tensors for tensor input, numpy otherwise."""
+        as_numpy = not isinstance(x, torch.Tensor)
+        if as_numpy:
+            x = torch.from_numpy(np.ascontiguousarray(x)).to(self.model.device)
+        probs, gender, feat = self.model.forward(x, True, True, graph=graph)
+        age = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        dev = x.device.index or 0
+        check(lib.hfr_age_gender_post(probs.data_ptr(), x.shape[0], probs.shape[1], age.data_ptr(), dev,
+                                      _stream_ptr(x.device)))
+        if as_numpy:
+            return age.cpu().numpy(), gender.cpu().numpy(), feat.cpu().numpy(), probs.cpu().numpy()
+        return age, gender, feat, probs
+
+    # -- reference-compatible closure -------------------------------------------------------------------
+    def load_age_gender(self, sess=None, graph=None):
+        w, h = self.model.w, self.model.h
+
+        def age_gender_fun(img):
+            import cv2
+            resized_image = cv2.resize(img, (w, h))
+            age, gender, feat, probs = self.age_gender_batch(np.ascontiguousarray(resized_image)[None])
+            if self.print_stat:
+                idx = probs[0].argsort()[::-1][:2]
+                print('gender', gender[0])
+                print('age', age[0])
+                print(idx, probs[0][idx], probs[0][idx] / probs[0][idx].sum())
+            return float(age[0]), gender[0], feat[0]
+        return age_gender_fun

@@ -1,0 +1,128 @@
+"""Drop-in for the reference's classifier: KNeighborsClassifier(n_neighbors=1, p=2) (facerec_test.py:272,422), used
+through the sklearn estimator protocol by classifier_tester / cross_validate (facerec_test.py:200-207) and by direct
+fit/predict (facerec_test.py:282-287,434-442); also valid as the last step of a Pipeline (facerec_test.py:271,421).
+
+fit stores the gallery on the GPU (row-sharded across ranks when a torch.distributed process group is given);
+predict runs the fused distance-GEMM + argmin kernel and, for a sharded gallery, merges the per-rank
+(distance, index) pairs after one all-gather over NCCL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator, ClassifierMixin
+
+from . import _lib
+from ._lib import check, lib
+from .model import _stream_ptr
+
+
+class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
+    def __init__(self, n_neighbors=1, p=2, *, device="cuda:0", precision="bf16", process_group=None, sharded=False):
+        self.n_neighbors = n_neighbors
+        self.p = p
+        self.device = device
+        self.precision = precision
+        self.process_group = process_group
+        self.sharded = sharded
+
+    # -- helpers --------------------------------------------------------------------------------------
+    def _dev(self):
+        return torch.device(self.device)
+
+    def _to_dev(self, X):
+        if isinstance(X, torch.Tensor):
+            t = X.to(self._dev(), torch.float32)
+        else:
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError(f"Expected 2D array, got {X.ndim}D array instead")
+            t = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(self._dev())
+        return t.contiguous()
+
+    def _free(self):
+        h = getattr(self, "_knn", None)
+        if h:
+            lib.hfr_knn_free(h)
+            self._knn = None
+
+    def __del__(self):
+        self._free()
+
+    # -- sklearn protocol -------------------------------------------------------------------------------
+    def fit(self, X, y):
+        """X: (N, D) gallery embeddings.  With sharded=True each rank passes ITS rows of the gallery (contiguous
+        blocks in rank order) and the labels of the whole gallery are all-gathered."""
+        if self.n_neighbors != 1 or self.p != 2:
+            raise ValueError("only n_neighbors=1, p=2 (the reference's 1-NN) runs on the GPU path")
+        if not torch.cuda.is_available():
+            raise _lib.HfrError("no CUDA device available; this classifier has no CPU fallback")
+        self._free()
+        g = self._to_dev(X)
+        y = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y)
+        if g.shape[0] != y.shape[0]:
+            raise ValueError("X and y have inconsistent numbers of samples")
+        if g.shape[0] == 0:
+            raise ValueError("Found array with 0 sample(s)")
+        self._pad = (-g.shape[1]) % 8  # TMA rows must be multiples of 16 bytes: zero-pad odd dimensions (e.g. PCA)
+        if self._pad:
+            g = torch.nn.functional.pad(g, (0, self._pad))
+        self.n_features_in_ = int(g.shape[1] - self._pad)
+        offset = 0
+        if self.sharded:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+            counts = [None] * world
+            dist.all_gather_object(counts, int(g.shape[0]), group=self.process_group)
+            labels = [None] * world
+            dist.all_gather_object(labels, y, group=self.process_group)
+            offset = int(sum(counts[:rank]))
+            y = np.concatenate(labels)
+        self.classes_, self._y = np.unique(y, return_inverse=True)
+        self._labels = y
+        self._gallery = g  # keeps the fp32 rows alive: the kernel re-ranks its candidates against them
+        h = C.c_void_p()
+        dev = self._dev().index or 0
+        check(lib.hfr_knn_create(dev, g.shape[1], _lib.PREC[self.precision], C.byref(h)))
+        self._knn = h
+        check(lib.hfr_knn_set_gallery(h, g.data_ptr(), g.shape[0], offset, _stream_ptr(g.device)))
+        return self
+
+    def kneighbors(self, X, n_neighbors=None, return_distance=True):
+        if getattr(self, "_knn", None) is None:
+            from sklearn.exceptions import NotFittedError
+            raise NotFittedError("This KNeighborsClassifier instance is not fitted yet.")
+        if n_neighbors not in (None, 1):
+            raise ValueError("only the nearest neighbour is computed")
+        q = self._to_dev(X)
+        if q.shape[1] != self.n_features_in_:
+            raise ValueError(f"X has {q.shape[1]} features, but KNeighborsClassifier is expecting "
+                             f"{self.n_features_in_} features as input")
+        if self._pad:
+            q = torch.nn.functional.pad(q, (0, self._pad))
+        nq = q.shape[0]
+        d2 = torch.empty(nq, dtype=torch.float32, device=q.device)
+        idx = torch.empty(nq, dtype=torch.int64, device=q.device)
+        dev = q.device.index or 0
+        stream = _stream_ptr(q.device)
+        check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, d2.data_ptr(), idx.data_ptr(), stream))
+        if self.sharded:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+            d_all = torch.empty(world * nq, dtype=torch.float32, device=q.device)
+            i_all = torch.empty(world * nq, dtype=torch.int64, device=q.device)
+            dist.all_gather_into_tensor(d_all, d2, group=self.process_group)
+            dist.all_gather_into_tensor(i_all, idx, group=self.process_group)
+            check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), world, nq, d2.data_ptr(), idx.data_ptr(), dev,
+                                    stream))
+        self._last_idx = idx
+        ind = idx.cpu().numpy().reshape(-1, 1)
+        if return_distance:
+            return np.sqrt(np.maximum(d2.cpu().numpy().astype(np.float64), 0.0)).reshape(-1, 1), ind
+        return ind
+
+    def predict(self, X):
+        ind = self.kneighbors(X, return_distance=False)[:, 0]
+        return self._labels[ind]

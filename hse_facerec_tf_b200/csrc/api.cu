@@ -109,12 +109,18 @@ struct hfr_model {
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  // per-layer timing (eager mode only): event pairs around every layer launch
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;           // 2 per layer, re-used every step
+  std::vector<double> layer_ms;
+  int timed_steps = 0;
   // host-buffer path staging
   DevBuf stage_in;
   std::vector<std::unique_ptr<DevBuf>> stage_out;
 
   ~hfr_model() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    for (auto e : ev) cudaEventDestroy(e);
     for (auto& d : dev) {
       if (d.w) cudaFree(d.w);
       if (d.bias) cudaFree(d.bias);
@@ -226,6 +232,7 @@ struct hfr_model {
       void* out = val_ptr(L.out, batch);
       const int act = L.act;  // A_NONE/A_RELU/A_RELU6 share values with the kernels' ACT_* codes
       const int round_out = rt && feeds_tensor_core(L.out);
+      if (timing) cuda_check(cudaEventRecord(ev[2 * i], s), "cudaEventRecord");
       switch (L.kind) {
         case L_STEM: {
           StemArgs a;
@@ -290,6 +297,17 @@ struct hfr_model {
         default:
           throw Error(HFR_ERR_UNSUPPORTED, "internal: unknown layer kind");
       }
+      if (timing) cuda_check(cudaEventRecord(ev[2 * i + 1], s), "cudaEventRecord");
+    }
+    if (timing) {
+      // read back the previous step's events lazily would need double buffering; steps under timing are few, so sync
+      cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize(timing)");
+      for (size_t i = 0; i < plan.layers.size(); ++i) {
+        float ms = 0.f;
+        cuda_check(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]), "cudaEventElapsedTime");
+        layer_ms[i] += ms;
+      }
+      ++timed_steps;
     }
     for (size_t o = 0; o < plan.outputs.size(); ++o) {
       const int v = plan.outputs[o];
@@ -314,14 +332,14 @@ struct hfr_model {
     use_device(device);
     ensure_arena(batch);
     last_batch = batch;
-    if (!(flags & HFR_FLAG_CUDA_GRAPH) || s == nullptr) {
+    if (!(flags & HFR_FLAG_CUDA_GRAPH) || s == nullptr || timing) {
       run_layers(x, in_dtype, batch, flags, outs, s);
       return;
     }
     GraphKey key{x, in_dtype, batch, flags, std::vector<void*>(outs, outs + plan.outputs.size())};
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-      if (graphs.size() >= 16) {
+      if (graphs.size() >= 64) {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         graphs.clear();
       }
@@ -479,6 +497,28 @@ int hfr_model_set_keep_activations(hfr_model* m, int keep) {
     m->plan_arena();
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
     m->graphs.clear();
+  });
+}
+
+int hfr_model_set_layer_timing(hfr_model* m, int enable) {
+  return guarded([&] {
+    if (!m || m->device < 0) throw Error(HFR_ERR_INVALID, "needs a GPU model handle");
+    use_device(m->device);
+    if (enable && m->ev.empty()) {
+      m->ev.resize(2 * m->plan.layers.size());
+      for (auto& e : m->ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    }
+    m->timing = enable != 0;
+    m->layer_ms.assign(m->plan.layers.size(), 0.0);
+    m->timed_steps = 0;
+  });
+}
+
+int hfr_model_get_layer_times(const hfr_model* m, double* ms_per_layer, int* steps) {
+  return guarded([&] {
+    if (!m || !ms_per_layer) throw Error(HFR_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < m->layer_ms.size(); ++i) ms_per_layer[i] = m->layer_ms[i];
+    if (steps) *steps = m->timed_steps;
   });
 }
 

@@ -88,6 +88,10 @@ int hfr_model_set_keep_activations(hfr_model* m, int keep);
 /* Intermediate activation of layer `layer_index` (plan order) from the last forward, converted to float32 NHWC on the
  * device; for layer-by-layer parity checks.  Returns the element count per image, or a negative status. */
 int64_t hfr_model_debug_layer(hfr_model* m, int layer_index, int batch, float* dst, void* stream);
+/* Per-layer device timing: while enabled, forward runs eagerly with a CUDA-event pair around every layer launch (on
+ * the caller's stream) and accumulates the durations; get returns the sums in ms (plan order) and the step count. */
+int hfr_model_set_layer_timing(hfr_model* m, int enable);
+int hfr_model_get_layer_times(const hfr_model* m, double* ms_per_layer, int* steps);
 void hfr_model_free(hfr_model* m);
 
 /* age = 1 + sum_{i in top2} i * p_i / sum_{top2} p   (facial_analysis.py:113-124); age_probs [batch, n] float32. */

@@ -1,0 +1,72 @@
+"""Graph compiler (C++ host code behind hfr_model_load, device=-1) checked without a GPU: the fused plan, executed on
+the CPU with the folded weights the library exports, must reproduce the oracle's evaluation of the original graph."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hse_facerec_tf_b200 as hfr
+from hse_facerec_tf_b200 import _lib
+from oracle.tfnet import GraphOracle, preprocess_rgb_u8
+from tests.helpers import cosine, run_plan_cpu
+
+OUTS = ["age_pred/Softmax:0", "gender_pred/Sigmoid:0", "global_pooling/Mean:0"]
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(os.path.dirname(_lib.__file__), "..", "include", "hfr.h")).read()
+    declared = set(re.findall(r"\b(hfr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/hfr.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.hfr_version() >= 100
+
+
+def test_plan_of_real_graph(age_gender_pb):
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", OUTS, device=None)
+    assert (m.h, m.w, m.c) == (224, 224, 3) and m.out_dims == [100, 1, 1024]
+    layers = m.plan()["layers"]
+    kinds = [L["kind"] for L in layers]
+    assert kinds == ["stem"] + ["dw", "pw"] * 13 + ["gap", "fc", "fc", "fc"]
+    assert [L["stride"] for L in layers if L["kind"] == "dw"] == [1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1]
+    assert all(L["act"] == "relu6" for L in layers[:27])
+    assert [L["act"] for L in layers[27:]] == ["none", "relu", "softmax", "sigmoid"]
+    # TF SAME at stride 2 on even sizes: 0 before, 1 after
+    assert layers[0]["pad"] == [0, 1, 0, 1] and layers[3]["pad"] == [0, 1, 0, 1] and layers[1]["pad"] == [1, 1, 1, 1]
+    assert [L["cout"] for L in layers if L["kind"] == "pw"] == [64, 128, 128, 256, 256] + [512] * 6 + [1024, 1024]
+
+
+@pytest.mark.parametrize("size", [224, 192])
+def test_compiled_plan_matches_oracle(age_gender_pb, golden_dir, size):
+    crops = np.load(f"{golden_dir}/face_crops_u8.npz")[f"c{size}"][:2]
+    noise = np.random.RandomState(0).randint(0, 256, (1, size, size, 3)).astype(np.uint8)
+    x = preprocess_rgb_u8(np.concatenate([noise, crops]))
+    outs = OUTS if size == 224 else OUTS[2:]
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", outs, device=None, input_hw=0 if size == 224 else size)
+    got, _ = run_plan_cpu(m, x)
+    ref = GraphOracle(age_gender_pb).run(outs, {"input_1:0": x})
+    for g, r in zip(got, ref):
+        np.testing.assert_allclose(g, r.reshape(g.shape), rtol=2e-3, atol=2e-5)
+    assert cosine(got[-1], ref[-1].reshape(got[-1].shape)).min() > 0.999999
+
+
+def test_error_mapping(age_gender_pb, tmp_path):
+    with pytest.raises(KeyError):
+        hfr.HfrModel(age_gender_pb, "input_1:0", ["no_such_tensor:0"], device=None)
+    with pytest.raises(KeyError):
+        hfr.HfrModel(age_gender_pb, "no_such_input:0", OUTS, device=None)
+    with pytest.raises(FileNotFoundError):
+        hfr.HfrModel(str(tmp_path / "missing.pb"), "input_1:0", OUTS, device=None)
+    bad = tmp_path / "bad.pb"
+    bad.write_bytes(b"\xff\xff\xff\xff not a graphdef")
+    with pytest.raises(ValueError):
+        hfr.HfrModel(str(bad), "input_1:0", OUTS, device=None)
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", OUTS, device=None)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(hfr.HfrError):   # no CPU fallback: a GPU handle cannot be created here
+            hfr.HfrModel(age_gender_pb, "input_1:0", OUTS, device="cuda:0")

@@ -1,0 +1,159 @@
+"""Kernel-level parity (through the C ABI single-operator entry points) against plain torch fp32 references."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hse_facerec_tf_b200 import _lib
+from hse_facerec_tf_b200._lib import check, lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TDT = {0: torch.float32, 1: torch.float32, 2: torch.bfloat16}
+
+
+def _stream():
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def tf32_round(t):
+    """round-to-nearest-even to 10 mantissa bits"""
+    u = t.contiguous().view(torch.int32)
+    u = (u + 0x0FFF + ((u >> 13) & 1)) & ~0x1FFF
+    return u.view(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    (128, 64, 32), (128, 64, 64), (300, 128, 256), (1000, 256, 1024), (4096, 512, 512), (12544, 64, 32),
+    (2304, 1024, 512), (130, 1024, 1024), (77, 128, 128), (50176, 128, 64),
+]
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias_act(prec, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    dt = TDT[prec]
+    if prec == 1:
+        a, b = tf32_round(a), tf32_round(b)
+    a_t, b_t, res_t = a.to(dt).contiguous(), b.to(dt).contiguous(), res.to(dt).contiguous()
+    for act, use_res in ((0, False), (2, False), (1, True)):
+        y = torch.full((M, N), float("nan"), dtype=dt, device=DEV)
+        check(lib.hfr_op_gemm_bias_act(a_t.data_ptr(), b_t.data_ptr(), bias.data_ptr(), _ptr(res_t) if use_res else None,
+                                       y.data_ptr(), M, N, K, act, prec, 0, _stream()))
+        torch.cuda.synchronize()
+        ref = a_t.double() @ b_t.double().t() + bias.double()
+        if use_res:
+            ref = ref + res_t.double()
+        if act == 1:
+            ref = torch.relu(ref)
+        if act == 2:
+            ref = torch.clamp(ref, 0, 6)
+        got = y.double()
+        assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+        # operands are exactly representable, accumulation is fp32: only the output rounding differs
+        tol = 2e-2 if prec == 2 else 2e-4
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item() + 1.0
+        assert err <= tol * scale, f"M={M} N={N} K={K} prec={prec} act={act}: max err {err} (scale {scale})"
+
+
+# ------------------------------------------------------------------------------------------------ depthwise
+DW_CASES = [  # (B, H, W, C, stride)
+    (2, 16, 16, 32, 1), (2, 16, 16, 64, 2), (3, 12, 12, 128, 1), (2, 14, 14, 512, 2), (2, 7, 7, 1024, 1),
+    (1, 6, 6, 256, 1), (2, 96, 96, 32, 1), (1, 112, 112, 64, 2), (2, 13, 9, 64, 2), (2, 24, 24, 256, 1),
+]
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("B,H,W,C,stride", DW_CASES)
+def test_dwconv3x3(prec, B, H, W, C, stride):
+    g = torch.Generator(device="cpu").manual_seed(H * 31 + C + stride)
+    dt = TDT[prec]
+    x = torch.randn(B, H, W, C, generator=g).to(DEV).to(dt).contiguous()
+    w = torch.randn(9, C, generator=g).to(DEV)
+    bias = torch.randn(C, generator=g).to(DEV)
+    ho, wo = -(-H // stride), -(-W // stride)
+    pt = max((ho - 1) * stride + 3 - H, 0) // 2
+    pl = max((wo - 1) * stride + 3 - W, 0) // 2
+    pb = max((ho - 1) * stride + 3 - H, 0) - pt
+    pr = max((wo - 1) * stride + 3 - W, 0) - pl
+    y = torch.full((B, ho, wo, C), float("nan"), dtype=dt, device=DEV)
+    check(lib.hfr_op_dwconv3x3(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, C, stride, pt, pl, ho,
+                               wo, 2, prec, 0, _stream()))
+    torch.cuda.synchronize()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    ref = F.conv2d(xp, w.view(3, 3, C).permute(2, 0, 1).unsqueeze(1), bias, stride=stride, groups=C)
+    ref = torch.clamp(ref, 0, 6).permute(0, 2, 3, 1)
+    got = y.float()
+    assert torch.isfinite(got).all()
+    tol = 4e-2 if prec == 2 else 1e-4
+    assert (got - ref).abs().max().item() <= tol
+
+
+# ------------------------------------------------------------------------------------------------ stem
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("case", [(2, 32, 32, 3, 2, 32, "u8"), (2, 30, 30, 3, 2, 32, "f32"), (1, 38, 38, 7, 2, 64, "u8")])
+def test_stem_conv(prec, case):
+    B, H, W, k, stride, cout, kind = case
+    g = torch.Generator(device="cpu").manual_seed(H + k)
+    dt = TDT[prec]
+    w = (torch.randn(k, k, 3, cout, generator=g) * 0.03).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ho, wo = -(-H // stride), -(-W // stride)
+    tot_h = max((ho - 1) * stride + k - H, 0)
+    tot_w = max((wo - 1) * stride + k - W, 0)
+    pt, pl = tot_h // 2, tot_w // 2
+    if kind == "u8":
+        x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(DEV)
+        flags = _lib.FLAG_BGR | _lib.FLAG_MEAN_IMAGENET
+        xf = x.float().flip(-1) - torch.tensor([103.939, 116.779, 123.68], device=DEV)
+        in_dt = 1
+    else:
+        x = (torch.randn(B, H, W, 3, generator=g) * 60).to(DEV)
+        flags, xf, in_dt = 0, x, 0
+    y = torch.full((B, ho, wo, cout), float("nan"), dtype=dt, device=DEV)
+    check(lib.hfr_op_stem_conv(x.data_ptr(), in_dt, w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, k, k, stride,
+                               pt, pl, ho, wo, cout, flags, 2, prec, 0, _stream()))
+    torch.cuda.synchronize()
+    xp = F.pad(xf.permute(0, 3, 1, 2), (pl, tot_w - pl, pt, tot_h - pt))
+    ref = torch.clamp(F.conv2d(xp, w.permute(3, 2, 0, 1), bias, stride=stride), 0, 6).permute(0, 2, 3, 1)
+    got = y.float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= (4e-2 if prec == 2 else 2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def test_l2_normalize_matches_sklearn():
+    from sklearn import preprocessing
+    x = np.random.RandomState(0).randn(1000, 1024).astype(np.float32)
+    x[5] = 0
+    from hse_facerec_tf_b200 import normalize
+    got = normalize(x)
+    ref = preprocessing.normalize(x, norm="l2")
+    assert got.dtype == np.float32 and (got[5] == 0).all()
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-8)
+
+
+def test_age_post_matches_reference_rule():
+    from oracle.tfnet import age_from_probs
+    rs = np.random.RandomState(1)
+    p = rs.dirichlet(np.ones(100) * 0.3, size=257).astype(np.float32)
+    p[0, :] = 0
+    p[0, [10, 20, 30]] = [0.3, 0.3, 0.1]   # exact tie -> higher index first
+    t = torch.from_numpy(p).to(DEV)
+    age = torch.empty(p.shape[0], device=DEV)
+    check(lib.hfr_age_gender_post(t.data_ptr(), p.shape[0], 100, age.data_ptr(), 0, _stream()))
+    ref = np.array([age_from_probs(r)[0] for r in p])
+    np.testing.assert_allclose(age.cpu().numpy(), ref, rtol=1e-5)

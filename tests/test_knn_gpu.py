@@ -1,0 +1,131 @@
+"""1-NN identification parity against the reference's own dependency (scikit-learn KNeighborsClassifier, the real
+implementation - facerec_test.py:272,284-285) on seeded galleries."""
+import numpy as np
+import pytest
+import torch
+from sklearn import neighbors, preprocessing
+
+import hse_facerec_tf_b200 as hfr
+
+pytestmark = pytest.mark.gpu
+
+
+def make_problem(n, nq, d, seed=0, normalised=True, sigma=0.05):
+    rs = np.random.RandomState(seed)
+    g = rs.randn(n, d).astype(np.float32)
+    if normalised:
+        g = preprocessing.normalize(g)
+    else:
+        g *= rs.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)   # exercises the ||g||^2 term
+    pick = np.random.RandomState(seed + 1).randint(0, n, nq)
+    q = g[pick] + sigma * np.random.RandomState(seed + 2).randn(nq, d).astype(np.float32)
+    if normalised:
+        q = preprocessing.normalize(q)
+    return g, q.astype(np.float32), pick
+
+
+def sk_margins(g, q):
+    nn = neighbors.NearestNeighbors(n_neighbors=2, algorithm="brute").fit(g)
+    dist, ind = nn.kneighbors(q)
+    return dist, ind
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("n,nq,d,normalised", [(5000, 300, 1024, True), (20000, 1000, 2048, True),
+                                               (3000, 257, 128, False), (70000, 700, 1024, False), (1, 5, 64, True)])
+def test_kneighbors_matches_sklearn(precision, n, nq, d, normalised):
+    g, q, pick = make_problem(n, nq, d, seed=n % 97, normalised=normalised)
+    y = np.arange(n) % 1000
+    clf = hfr.KNeighborsClassifier(n_neighbors=1, p=2, precision=precision).fit(g, y)
+    dist, ind = clf.kneighbors(q)
+    sk = neighbors.KNeighborsClassifier(n_neighbors=1, p=2).fit(g, y)
+    sk_d, sk_i = sk.kneighbors(q)
+    if n >= 2:
+        d2, _ = sk_margins(g, q)
+        clear = (d2[:, 1] - d2[:, 0]) > 1e-6          # stated tolerance: fp64 re-rank => only exact ties are excluded
+    else:
+        clear = np.ones(nq, bool)
+    assert clear.mean() > 0.99
+    np.testing.assert_array_equal(ind[clear], sk_i[clear])
+    np.testing.assert_allclose(dist[clear], sk_d[clear], rtol=1e-4, atol=2e-4)
+    np.testing.assert_array_equal(clf.predict(q)[clear], sk.predict(q)[clear])
+
+
+def test_hard_queries_random_margins():
+    """Random (not planted) queries: top-2 margins are tiny; the fp32/fp64 re-rank of the bf16 candidates must still
+    agree with sklearn wherever the margin exceeds 1e-5."""
+    rs = np.random.RandomState(5)
+    g = preprocessing.normalize(rs.randn(40000, 1024).astype(np.float32))
+    q = preprocessing.normalize(rs.randn(2000, 1024).astype(np.float32))
+    clf = hfr.KNeighborsClassifier(precision="bf16").fit(g, np.arange(len(g)))
+    ind = clf.kneighbors(q, return_distance=False)[:, 0]
+    d2, i2 = sk_margins(g, q)
+    clear = (d2[:, 1] - d2[:, 0]) > 1e-5
+    agree = (ind == i2[:, 0])
+    assert agree[clear].mean() > 0.995, agree[clear].mean()   # candidates come from a bf16 top-2 per 16k-row split
+
+
+def test_exact_duplicates_tie_to_lowest_index():
+    rs = np.random.RandomState(2)
+    g = rs.randn(1200, 256).astype(np.float32)
+    g[500] = g[10]
+    g[900] = g[10]
+    clf = hfr.KNeighborsClassifier(precision="tf32").fit(g, np.arange(1200))
+    assert clf.predict(g[10:11])[0] == 10
+
+
+def test_sklearn_protocol(tmp_path):
+    from sklearn import model_selection
+    from sklearn.base import clone
+    from sklearn.decomposition import PCA
+    from sklearn.pipeline import Pipeline
+    g, q, pick = make_problem(2000, 10, 256, seed=3)
+    y = np.repeat(np.arange(500), 4)
+    X = preprocessing.normalize(g + 0.0)
+    clf = hfr.KNeighborsClassifier(n_neighbors=1, p=2)
+    assert clone(clf).get_params()["n_neighbors"] == 1
+    # the reference's evaluation protocol, facerec_test.py:200-207
+    sss = model_selection.StratifiedShuffleSplit(n_splits=1, test_size=0.5, random_state=0)
+    ours = model_selection.cross_validate(clf, X, y, scoring="accuracy", cv=sss)["test_score"]
+    ref = model_selection.cross_validate(neighbors.KNeighborsClassifier(n_neighbors=1, p=2), X, y, scoring="accuracy",
+                                         cv=sss)["test_score"]
+    np.testing.assert_allclose(ours, ref)
+    pipe = Pipeline([("pca", PCA(n_components=20, random_state=0)), ("classifier", hfr.KNeighborsClassifier(1, 2))])
+    ref_pipe = Pipeline([("pca", PCA(n_components=20, random_state=0)),
+                         ("classifier", neighbors.KNeighborsClassifier(n_neighbors=1, p=2))])
+    assert (pipe.fit(X[::2], y[::2]).predict(X[1::2]) == ref_pipe.fit(X[::2], y[::2]).predict(X[1::2])).mean() > 0.99
+    with pytest.raises(Exception):
+        hfr.KNeighborsClassifier().predict(X)
+
+
+def test_merge_of_shards_equals_single_gallery():
+    """Gallery row-sharded over 4 handles on one GPU + hfr_knn_merge == one handle over the whole gallery."""
+    import ctypes as C
+    from hse_facerec_tf_b200._lib import check, lib
+    g, q, _ = make_problem(10000, 500, 512, seed=9)
+    whole = hfr.KNeighborsClassifier(precision="bf16").fit(g, np.arange(len(g)))
+    d_ref, i_ref = whole.kneighbors(q)
+    parts = np.array_split(np.arange(len(g)), 4)
+    d_all, i_all = [], []
+    qt = torch.from_numpy(q).cuda()
+    keep = []
+    for p in parts:
+        gt = torch.from_numpy(g[p]).cuda()
+        h = C.c_void_p()
+        check(lib.hfr_knn_create(0, 512, 2, C.byref(h)))
+        check(lib.hfr_knn_set_gallery(h, gt.data_ptr(), len(p), int(p[0]), None))
+        d = torch.empty(len(q), device="cuda")
+        i = torch.empty(len(q), dtype=torch.int64, device="cuda")
+        check(lib.hfr_knn_query(h, qt.data_ptr(), len(q), d.data_ptr(), i.data_ptr(), None))
+        d_all.append(d)
+        i_all.append(i)
+        keep.append((gt, h))
+    torch.cuda.synchronize()
+    D, I = torch.stack(d_all).contiguous(), torch.stack(i_all).contiguous()
+    bd = torch.empty(len(q), device="cuda")
+    bi = torch.empty(len(q), dtype=torch.int64, device="cuda")
+    check(lib.hfr_knn_merge(D.data_ptr(), I.data_ptr(), 4, len(q), bd.data_ptr(), bi.data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(bi.cpu().numpy(), i_ref[:, 0])
+    for gt, h in keep:
+        lib.hfr_knn_free(h)

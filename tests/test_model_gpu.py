@@ -1,0 +1,138 @@
+"""Whole-network parity on the GPU: the reference's only shipped model (age/gender MobileNet-224 + heads, which is
+also the VGGFace2 identity MobileNet) against the CPU oracle, at 224 and at 192 (BASELINE config 1 stand-in)."""
+import numpy as np
+import pytest
+import torch
+
+import hse_facerec_tf_b200 as hfr
+from oracle.tfnet import GraphOracle, age_from_probs, preprocess_rgb_u8
+from tests.helpers import cosine, run_plan_cpu, smooth_images
+
+pytestmark = pytest.mark.gpu
+OUTS = ["age_pred/Softmax:0", "gender_pred/Sigmoid:0", "global_pooling/Mean:0"]
+# stated tolerances: cosine of the 1024-D embedding vs the fp32 CPU oracle, for rows whose oracle norm is > 1
+COS_MIN = {"fp32": 0.99999, "tf32": 0.9999, "bf16": 0.995}
+
+
+def _inputs(golden_dir, size, n_crops=8):
+    crops = np.load(f"{golden_dir}/face_crops_u8.npz")[f"c{size}"][:n_crops]
+    noise = np.random.RandomState(0).randint(0, 256, (2, size, size, 3)).astype(np.uint8)
+    return np.concatenate([noise, smooth_images(3, size, 7), crops])
+
+
+@pytest.fixture(scope="module")
+def ref224(age_gender_pb, golden_dir):
+    u8 = _inputs(golden_dir, 224)
+    a, g, f = GraphOracle(age_gender_pb).run(OUTS, {"input_1:0": preprocess_rgb_u8(u8)})
+    return u8, a, g, f
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_layerwise_first_mismatch(age_gender_pb, golden_dir, precision):
+    """Localises a wrong kernel: every layer's GPU output against the CPU execution of the same plan."""
+    u8 = _inputs(golden_dir, 224, n_crops=2)[[0, 2, 5]]
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", OUTS, precision=precision)
+    m.keep_activations(True)
+    x = torch.from_numpy(u8).cuda()
+    m.forward(x)
+    torch.cuda.synchronize()
+    _, kept = run_plan_cpu(m, preprocess_rgb_u8(u8), keep=True)
+    tol = {"fp32": 2e-3, "tf32": 2e-2, "bf16": 0.25}[precision]
+    for li, L in enumerate(m.plan()["layers"]):
+        got = m.layer_output(li, u8.shape[0]).cpu().numpy().reshape(kept[li].shape)
+        assert np.isfinite(got).all(), f"layer {li} {L['name']}: non-finite"
+        err = np.abs(got - kept[li]).max()
+        scale = max(np.abs(kept[li]).max(), 1.0)
+        # errors compound with depth; the bound is on the running error relative to the activation range
+        assert err <= tol * scale * (1 + li / 4), f"layer {li} ({L['kind']} {L['name']}): max err {err}, scale {scale}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_age_gender_parity_224(age_gender_pb, ref224, precision):
+    u8, a_ref, g_ref, f_ref = ref224
+    fp = hfr.FacialImageProcessing(age_gender_pb, precision=precision)
+    age, gender, feat, probs = fp.age_gender_batch(torch.from_numpy(u8).cuda())
+    age, gender, feat, probs = (t.cpu().numpy() for t in (age, gender, feat, probs))
+    cos = cosine(feat, f_ref)
+    strong = np.linalg.norm(f_ref, axis=1) > 1
+    assert cos[strong].min() >= COS_MIN[precision], cos
+    print(f"[{precision}] cosine min {cos[strong].min():.6f}  max|d emb| {np.abs(feat - f_ref).max():.4g} "
+          f"max|d gender| {np.abs(gender - g_ref).max():.4g}")
+    if precision != "bf16":
+        # age top-2 index pair and the >= 0.6 gender decision must match exactly
+        for i in range(len(u8)):
+            ref_age, ref_idx = age_from_probs(a_ref[i])
+            top2 = probs[i].argsort()[::-1][:2]
+            margin = np.sort(a_ref[i])[-2] - np.sort(a_ref[i])[-3]
+            if margin > 1e-3:
+                assert set(top2) == set(ref_idx)
+                assert abs(age[i] - ref_age) < 0.05
+            if abs(g_ref[i, 0] - 0.6) > 1e-2:
+                assert (gender[i, 0] >= 0.6) == (g_ref[i, 0] >= 0.6)
+        np.testing.assert_allclose(gender, g_ref, atol=5e-3)
+    else:
+        np.testing.assert_allclose(gender, g_ref, atol=0.08)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_embedding_parity_192_u8_and_f32_inputs(age_gender_pb, golden_dir, precision):
+    """BASELINE config 1 stand-in: the real MobileNet body run at 192x192; uint8 input with fused pre-processing
+    must equal float32 input pre-processed on the host (what the reference feeds)."""
+    u8 = _inputs(golden_dir, 192)
+    x = preprocess_rgb_u8(u8)
+    (f_ref,) = GraphOracle(age_gender_pb).run(OUTS[2:], {"input_1:0": x})
+    tfi = hfr.TensorFlowInference(age_gender_pb, "input_1:0", "global_pooling/Mean:0", precision=precision, input_hw=192)
+    assert (tfi.w, tfi.h) == (192, 192)
+    e_u8 = tfi.extract_batch(torch.from_numpy(u8).cuda()).cpu().numpy()
+    e_f32 = tfi.extract_batch(torch.from_numpy(x).cuda()).cpu().numpy()
+    e_host = tfi.extract_batch(u8)            # numpy in / numpy out path (H2D + D2H inside)
+    e_graph = tfi.extract_batch(torch.from_numpy(u8).cuda(), graph=True).cpu().numpy()
+    with torch.cuda.stream(torch.cuda.Stream()):
+        xs = torch.from_numpy(u8).cuda()
+        e_g1 = tfi.extract_batch(xs, graph=True).cpu().numpy()   # capture
+        e_g2 = tfi.extract_batch(xs, graph=True).cpu().numpy()   # replay
+    np.testing.assert_array_equal(e_u8, e_host)
+    np.testing.assert_array_equal(e_u8, e_graph)
+    np.testing.assert_array_equal(e_u8, e_g1)
+    np.testing.assert_array_equal(e_u8, e_g2)
+    np.testing.assert_allclose(e_u8, e_f32, rtol=1e-5, atol=1e-5)
+    strong = np.linalg.norm(f_ref, axis=1) > 1
+    cos = cosine(e_u8, f_ref)
+    assert cos[strong].min() >= COS_MIN[precision], cos
+    # L2-normalised output == sklearn normalize of the raw output
+    from sklearn import preprocessing
+    e_n = tfi.extract_batch(torch.from_numpy(u8).cuda(), l2norm=True).cpu().numpy()
+    np.testing.assert_allclose(e_n, preprocessing.normalize(e_u8), rtol=1e-5, atol=1e-7)
+
+
+def test_per_image_reference_api(age_gender_pb, golden_dir, tmp_path):
+    """extract_features(path) / age_gender_fun(img) keep the reference's per-image calling convention."""
+    from PIL import Image
+    crops = np.load(f"{golden_dir}/face_crops_u8.npz")["c224"]
+    p = tmp_path / "face.png"
+    Image.fromarray(crops[0]).save(p)
+    tfi = hfr.TensorFlowInference(age_gender_pb, "input_1:0", "global_pooling/Mean:0", precision="tf32")
+    f = tfi.extract_features(str(p))
+    assert f.shape == (1024,) and f.dtype == np.float32
+    x = tfi.preprocess_image(str(p), False)
+    (f_ref,) = GraphOracle(age_gender_pb).run(OUTS[2:], {"input_1:0": x[None].astype(np.float32)})
+    assert cosine(f[None], f_ref)[0] > 0.9999
+    tfi.close_session()
+    fp = hfr.FacialImageProcessing(age_gender_pb, precision="tf32")
+    age, gender, feat = fp.age_gender_fun(crops[0])
+    assert isinstance(age, float) and gender.shape == (1,) and feat.shape == (1024,)
+    assert abs(age - 36.757) < 0.1 and abs(gender[0] - 0.247) < 5e-3 and not fp.is_male(gender)[0]
+
+
+def test_batch_sizes_and_errors(age_gender_pb):
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", ["global_pooling/Mean:0"], precision="bf16", input_hw=192)
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.randint(0, 256, (70, 192, 192, 3)).astype(np.uint8)).cuda()
+    full = m.forward(x)[0]
+    for b in (1, 3, 64):
+        part = m.forward(x[:b].contiguous())[0]
+        torch.testing.assert_close(part, full[:b], rtol=0, atol=0)   # batch-invariant: same tiles, same order
+    with pytest.raises(ValueError):
+        m.forward(x[:, :100].contiguous())
+    with pytest.raises(ValueError):
+        m.forward(x.cpu())

@@ -146,7 +146,7 @@ def bench_network(args, rank, world, dev):
     stream = torch.cuda.Stream(device=dev)
     kw = dict(convert2BGR=spec["bgr"], imageNetUtilsMean=spec["imagenet"])
 
-    def step(i, graph=True):
+    def step(i, graph=not args.no_graph):
         model.forward(xs[i % nrot], graph=graph, outs=outs[i % nrot], **kw)
 
     import torch.distributed as dist
@@ -240,7 +240,7 @@ def bench_network(args, rank, world, dev):
                             input=f"{size}x{size}x3 uint8", parallelism=f"dp{world}",
                             l2_policy=f"inputs rotate over {nrot} distinct batches ({nrot * in_bytes / 1e6:.0f} MB > L2); "
                                       "activations (>= 0.4 GB/step written) exceed L2",
-                            cuda_graph=True),
+                            cuda_graph=not args.no_graph),
                 e2e=dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
                          d2h_bytes_per_step=out_bytes),
                 gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step),
@@ -401,6 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (queries for knn)")
     ap.add_argument("--gallery", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

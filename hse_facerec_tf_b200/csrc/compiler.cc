@@ -617,6 +617,7 @@ Plan compile_graph(const Graph& g, const CompileOptions& opt) {
       };
       while (uses[(size_t)cur].size() == 1 && !is_out[(size_t)cur]) {
         const int ni = uses[(size_t)cur][0];
+        if (absorbed[(size_t)ni]) break;  // e.g. the residual add already belongs to the other branch's convolution
         const IOp& nx = ops[(size_t)ni];
         bool took = true;
         if (nx.kind == IOp::SCALE && !has_act && !has_res) {

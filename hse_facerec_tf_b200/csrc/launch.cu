@@ -237,6 +237,14 @@ void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s) {
                    (const cuuint64_t*)strides, lower, upper, (cuuint32_t)bk, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(-6, "cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
+  {
+    // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers up to 13.1 encode im2col maps of
+    // tensors smaller than 128 KiB with a descriptor bit that must be cleared.
+    int drv = 0;
+    cuda_check(cudaDriverGetVersion(&drv), "cudaDriverGetVersion");
+    const uint64_t tensor_bytes = (uint64_t)a.B * a.H * a.W * a.cin * es;
+    if (drv <= 13010 && tensor_bytes < 131072) reinterpret_cast<uint64_t*>(&tA)[1] &= ~(1ull << 21);
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = a.cout; p.K = a.kh * a.kw * a.cin;

@@ -70,3 +70,44 @@ def test_error_mapping(age_gender_pb, tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(hfr.HfrError):   # no CPU fallback: a GPU handle cannot be created here
             hfr.HfrModel(age_gender_pb, "input_1:0", OUTS, device="cuda:0")
+
+
+def test_unfolded_keras_mobilenet_with_learning_phase(tmp_path):
+    """The format of the missing models/vgg2_mobilenet.pb (facerec_test.py:212): un-folded BN arithmetic under
+    Switch/Merge on the learning-phase placeholder, Reshape((1,1,1024)) output."""
+    from hse_facerec_tf_b200.synth import write_mobilenet_pb
+    pb = write_mobilenet_pb(str(tmp_path / "vgg2_mobilenet.pb"), seed=3, input_hw=96)
+    args = dict(learning_phase_tensor="conv1_bn/keras_learning_phase:0", device=None)
+    m = hfr.HfrModel(pb, "input_1:0", ["reshape_1/Reshape:0"], **args)
+    assert (m.h, m.w) == (96, 96) and m.out_dims == [1024]
+    kinds = [L["kind"] for L in m.plan()["layers"]]
+    assert kinds == ["stem"] + ["dw", "pw"] * 13 + ["gap"]
+    x = preprocess_rgb_u8(np.random.RandomState(1).randint(0, 256, (2, 96, 96, 3)).astype(np.uint8))
+    (ref,) = GraphOracle(pb).run(["reshape_1/Reshape:0"], {"input_1:0": x, "conv1_bn/keras_learning_phase:0": False})
+    got, _ = run_plan_cpu(m, x)
+    np.testing.assert_allclose(got[0], ref.reshape(2, -1), rtol=1e-3, atol=1e-4)
+    with pytest.raises(ValueError):      # phase placeholder not named -> the conditional cannot be resolved
+        hfr.HfrModel(pb, "input_1:0", ["reshape_1/Reshape:0"], device=None)
+    # feeding the phase with 1 selects the (here: stand-in) training branch, as TF would
+    m1 = hfr.HfrModel(pb, "input_1:0", ["reshape_1/Reshape:0"], additional_input_value=1, **args)
+    got1, _ = run_plan_cpu(m1, x)
+    assert np.abs(got1[0] - got[0]).max() > 1.0
+
+
+def test_resnet50_caffe_style_plan(tmp_path):
+    """The format assumed for the missing models/vgg2_resnet.pb (facerec_test.py:213): Pad+VALID stem, explicit Pad in
+    front of the ceil-mode max pool, FusedBatchNorm, stride on the 1x1 reduce, residual Add -> Relu, 7x7 AvgPool."""
+    from collections import Counter
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    pb = write_resnet50_pb(str(tmp_path / "vgg2_resnet.pb"), seed=5)
+    m = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], device=None)
+    assert m.out_dims == [2048]
+    layers = m.plan()["layers"]
+    assert Counter(L["kind"] for L in layers) == {"pw": 36, "conv": 16, "subsample": 3, "stem": 1, "maxpool": 1, "gap": 1}
+    assert layers[0]["pad"] == [3, 3, 3, 3] and layers[0]["k"] == [7, 7] and layers[0]["hw_out"] == [112, 112]
+    assert layers[1]["kind"] == "maxpool" and layers[1]["explicit_zero_pad"] and layers[1]["hw_out"] == [56, 56]
+    assert sum(1 for L in layers if L["in2"] >= 0) == 16          # one fused residual add per bottleneck
+    x = preprocess_rgb_u8(np.random.RandomState(2).randint(0, 256, (1, 224, 224, 3)).astype(np.uint8), True, False)
+    (ref,) = GraphOracle(pb).run(["pool5_7x7_s1:0"], {"input:0": x})
+    got, _ = run_plan_cpu(m, x)
+    np.testing.assert_allclose(got[0], ref.reshape(1, -1), rtol=2e-3, atol=2e-4)

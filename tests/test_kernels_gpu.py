@@ -134,6 +134,53 @@ def test_stem_conv(prec, case):
     assert (got - ref).abs().max().item() <= (4e-2 if prec == 2 else 2e-3)
 
 
+# ------------------------------------------------------------------------------------------------ KxK conv / pool
+CONV_CASES = [  # (B, H, W, cin, cout, k, stride)
+    (2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1), (5, 7, 7, 512, 512, 3, 1),
+    (1, 9, 11, 64, 128, 3, 1), (2, 16, 16, 64, 64, 3, 2),
+]
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride", CONV_CASES)
+def test_conv2d_implicit_gemm(prec, B, H, W, cin, cout, k, stride):
+    g = torch.Generator(device="cpu").manual_seed(H * 13 + cin)
+    dt = TDT[prec]
+    x = torch.randn(B, H, W, cin, generator=g).to(DEV)
+    w = (torch.randn(cout, k, k, cin, generator=g) / (k * k * cin) ** 0.5).to(DEV)
+    if prec == 1:
+        x, w = tf32_round(x), tf32_round(w)
+    x, w = x.to(dt).contiguous(), w.to(dt).contiguous()
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ho, wo = -(-H // stride), -(-W // stride)
+    th, tw = max((ho - 1) * stride + k - H, 0), max((wo - 1) * stride + k - W, 0)
+    res = torch.randn(B, ho, wo, cout, generator=g).to(DEV).to(dt).contiguous()
+    y = torch.full((B, ho, wo, cout), float("nan"), dtype=dt, device=DEV)
+    check(lib.hfr_op_conv2d(x.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr(), y.data_ptr(), B, H, W, cin, k, k,
+                            stride, th // 2, tw // 2, ho, wo, cout, 1, prec, 0, _stream()))
+    torch.cuda.synchronize()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2))
+    ref = F.conv2d(xp.double(), w.double().permute(0, 3, 1, 2), bias.double(), stride=stride).permute(0, 2, 3, 1)
+    ref = torch.relu(ref + res.double())
+    got = y.double()
+    assert torch.isfinite(got).all()
+    tol = 2e-2 if prec == 2 else 2e-4
+    assert (got - ref).abs().max().item() <= tol * (ref.abs().max().item() + 1.0)
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("explicit_zero", [0, 1])
+def test_maxpool(prec, explicit_zero):
+    dt = TDT[prec]
+    x = (torch.randn(3, 112, 112, 64, generator=torch.Generator().manual_seed(4)) - 0.5).to(DEV).to(dt).contiguous()
+    y = torch.full((3, 56, 56, 64), float("nan"), dtype=dt, device=DEV)
+    check(lib.hfr_op_maxpool(x.data_ptr(), y.data_ptr(), 3, 112, 112, 64, 3, 2, 0, 0, 56, 56, explicit_zero, prec, 0, _stream()))
+    torch.cuda.synchronize()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1), value=0.0 if explicit_zero else -float("inf"))
+    ref = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+    assert torch.equal(y.float(), ref)
+
+
 # ------------------------------------------------------------------------------------------------ small ops
 def test_l2_normalize_matches_sklearn():
     from sklearn import preprocessing

@@ -138,3 +138,34 @@ def test_batch_sizes_and_errors(age_gender_pb):
         m.forward(x[:, :100].contiguous())
     with pytest.raises(ValueError):
         m.forward(x.cpu())
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_resnet50_synthetic_parity(precision, tmp_path):
+    """BASELINE config 2: Caffe-style VGGFace2 ResNet-50 topology in the reference's .pb format with seeded synthetic
+    weights (the real vgg2_resnet.pb is not shipped) - GPU vs the CPU oracle evaluating the same file."""
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    pb = write_resnet50_pb(str(tmp_path / "vgg2_resnet.pb"), seed=7)
+    u8 = np.concatenate([np.random.RandomState(0).randint(0, 256, (1, 224, 224, 3)).astype(np.uint8),
+                         smooth_images(2, 224, 11)])
+    x = preprocess_rgb_u8(u8, True, False)        # BGR + VGGFace2 mean (facerec_test.py:213)
+    (ref,) = GraphOracle(pb).run(["pool5_7x7_s1:0"], {"input:0": x})
+    ref = ref.reshape(3, -1)
+    tfi = hfr.TensorFlowInference(pb, "input:0", "pool5_7x7_s1:0", convert2BGR=True, imageNetUtilsMean=False,
+                                  precision=precision)
+    assert (tfi.w, tfi.h) == (224, 224) and tfi.model.out_dims == [2048]
+    got = tfi.extract_batch(torch.from_numpy(u8).cuda()).cpu().numpy()
+    cos = cosine(got, ref)
+    print(f"[resnet50 {precision}] cosine {cos}  max|d| {np.abs(got - ref).max():.4g} (ref max {np.abs(ref).max():.3g})")
+    assert cos.min() >= (0.9999 if precision == "tf32" else 0.995)
+    # layer-by-layer on the same file, to localise a wrong kernel
+    m = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    m.keep_activations(True)
+    m.forward(torch.from_numpy(u8[:2]).cuda(), True, False)
+    torch.cuda.synchronize()
+    _, kept = run_plan_cpu(m, x[:2], keep=True)
+    tol = {"tf32": 2e-2, "bf16": 0.25}[precision]
+    for li, L in enumerate(m.plan()["layers"]):
+        g = m.layer_output(li, 2).cpu().numpy().reshape(kept[li].shape)
+        err, scale = np.abs(g - kept[li]).max(), max(np.abs(kept[li]).max(), 1.0)
+        assert np.isfinite(g).all() and err <= tol * scale * (1 + li / 8), f"layer {li} {L['kind']} {L['name']}: {err} / {scale}"

@@ -82,6 +82,36 @@ def diag_dw():
                 print("   bad per output row:", bad.sum(dim=(0, 2, 3)).tolist(), " per col:", bad.sum(dim=(0, 1, 3)).tolist())
 
 
+def diag_conv():
+    for prec in (2, 1):
+        for (B, H, W, cin, cout, k, s) in [(1, 8, 8, 64, 64, 3, 1), (2, 12, 12, 64, 64, 3, 1), (3, 7, 7, 128, 64, 3, 1),
+                                           (2, 14, 14, 64, 128, 3, 1), (1, 16, 16, 64, 64, 3, 2), (2, 56, 56, 64, 64, 3, 1)]:
+            dt = TDT[prec]
+            g = torch.Generator().manual_seed(3)
+            x = torch.randint(-2, 3, (B, H, W, cin), generator=g).float().to(DEV).to(dt)
+            w = torch.randint(-1, 2, (cout, k, k, cin), generator=g).float().to(DEV).to(dt)   # [cout][kh*kw][cin]
+            ho, wo = -(-H // s), -(-W // s)
+            th, tw = max((ho - 1) * s + k - H, 0), max((wo - 1) * s + k - W, 0)
+            y = torch.full((B, ho, wo, cout), float("nan"), dtype=dt, device=DEV)
+            rc = lib.hfr_op_conv2d(x.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), B, H, W, cin, k, k, s, th // 2,
+                                   tw // 2, ho, wo, cout, 0, prec, 0, None)
+            torch.cuda.synchronize()
+            if rc:
+                print(f"conv prec={prec} {B}x{H}x{W}x{cin}->{cout} k{k} s{s}: rc={rc} {lib.hfr_last_error().decode()}")
+                continue
+            xp = F.pad(x.float().permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2))
+            ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), None, stride=s).permute(0, 2, 3, 1)
+            got = torch.nan_to_num(y.float(), nan=1e9)
+            bad = got != ref
+            print(f"conv prec={prec} {B}x{H}x{W}x{cin}->{cout} k{k} s{s}: mismatches={bad.sum().item()}/{bad.numel()}")
+            if bad.any():
+                print("   first bad (b,y,x,c):", bad.nonzero()[:6].tolist())
+                print("   bad per image:", bad.sum(dim=(1, 2, 3)).tolist(), " per out row (img0):", bad[0].sum(dim=(1, 2)).tolist(),
+                      " per out col (img0):", bad[0].sum(dim=(0, 2)).tolist())
+                print("   got[0,0,:4,0]", got[0, 0, :4, 0].tolist(), "ref", ref[0, 0, :4, 0].tolist(),
+                      " got[0,1,:4,0]", got[0, 1, :4, 0].tolist(), "ref", ref[0, 1, :4, 0].tolist())
+
+
 def diag_knn():
     import hse_facerec_tf_b200 as hfr
     for prec in ("bf16", "tf32"):
@@ -128,6 +158,6 @@ if __name__ == "__main__":
     for w in what:
         print(f"===== {w}")
         try:
-            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model}[w]()
+            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv}[w]()
         except Exception:
             traceback.print_exc()

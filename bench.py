@@ -118,6 +118,8 @@ def plan_work(plan, es):
         else:
             flops = 0.0
         in_b = hin * win * L["cin"] * (1 if kind == "stem" else es)
+        if kind == "subsample":
+            in_b = ho * wo * L["cin"] * es      # only every stride-th pixel is read
         out_b = ho * wo * L["cout"] * (4 if kind in ("gap", "fc") else es)
         if kind == "fc":
             in_b, out_b = L["cin"] * 4, L["cout"] * 4

@@ -613,8 +613,8 @@ int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist
     cudaStream_t s = (cudaStream_t)stream;
     int splits, per;
     knn_plan(nq, k->n_local, &splits, &per);
-    k->part_score.ensure((size_t)nq * splits * 2 * 4);
-    k->part_idx.ensure((size_t)nq * splits * 2 * 4);
+    k->part_score.ensure((size_t)nq * splits * 4 * 4);  // [nq][splits][2 warpgroups][top-2]
+    k->part_idx.ensure((size_t)nq * splits * 4 * 4);
     KnnGemmArgs a;
     a.nq = nq; a.n = k->n_local; a.d = k->dim; a.splits = splits; a.n_blocks_per_unit = per;
     a.gnorm = (const float*)k->g_norm.p;

@@ -3,7 +3,8 @@
 //   warp 0 (1 lane)  TMA producer: A/B k-blocks (128-byte rows, SWIZZLE_128B) into a STAGES-deep smem ring
 //   warp 1 (1 lane)  MMA issuer:   tcgen05.mma cta_group::1, M=128 x N=BLOCK_N, fp32 accumulators in TMEM (2 stages)
 //   warp 2           TMEM allocator
-//   warps 4..7       epilogue:     tcgen05.ld -> registers -> fused epilogue
+//   warps 4..11      epilogue:     two warpgroups ping-pong on tiles (accumulator stage g = tile & 1);
+//                                  tcgen05.ld -> registers -> fused epilogue
 //
 // Epilogues
 //   EPI_STORE  out = act(acc + bias[n] (+ residual[m,n]))  -> T, staged in swizzled smem, written with TMA stores.
@@ -35,8 +36,8 @@ struct GemmParams {
   int round_tf32;         // round stored fp32 values to tf32 (they feed the next tf32 GEMM)
   // EPI_KNN
   const float* gnorm;     // [N] squared norms of the gallery rows
-  float* part_score;      // [M][splits][2]
-  int* part_idx;          // [M][splits][2]
+  float* part_score;      // [M][splits][2 warpgroups][2]
+  int* part_idx;          // [M][splits][2 warpgroups][2]
   int splits;
   // AMODE_IM2COL (implicit GEMM over an NHWC tensor): k-block kb -> (tap, channel block)
   int conv_kw, conv_cblocks;   // taps along W, channel blocks (of BK elements) per tap
@@ -64,7 +65,7 @@ struct GemmSmem {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = (EPI == EPI_STORE) ? 2 * 128 * 128 : 2 * BLOCK_N * 4;
+  static constexpr int kEpiBytes = (EPI == EPI_STORE) ? 4 * 128 * 128 : 2 * BLOCK_N * 4;  // 2 warpgroups x 2 buffers
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kEpiBytes;
   static constexpr int kStagesMax = kBudget / kStageBytes;
   static constexpr int kStages = kStagesMax > 6 ? 6 : kStagesMax;
@@ -72,7 +73,7 @@ struct GemmSmem {
 };
 
 template <typename T, int BLOCK_N, int EPI, int AMODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   using TR = GemmTraits<T>;
@@ -211,48 +212,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int ew = warp - 4;           // == warp % 4: TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue: two warpgroups, ping-pong on tiles
+    // Warpgroup g (warps 4+4g .. 7+4g) drains accumulator stage g, i.e. every tile with (tile & 1) == g, while the
+    // other warpgroup drains the previous/next tile.  Warp w may touch TMEM lanes 32*(w%4) .. +31.
+    const int g = (warp - 4) >> 2;
+    const int ew = warp & 3;
     const int row = ew * 32 + lane;    // row within the 128-row tile
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    uint32_t tile = 0;
+    const uint32_t bar_id = 1 + g;     // named barrier of this warpgroup (128 threads)
+    const bool leader = (ew == 0 && lane == 0);
+    const uint32_t as = g;
+    uint32_t tile = 0, my_tiles = 0;
     if constexpr (EPI == EPI_STORE) {
       constexpr int CH_ELEMS = 128 / (int)sizeof(T);  // columns per 128-byte staging chunk (32 fp32 / 64 bf16)
       constexpr int NCHUNK = BLOCK_N / CH_ELEMS;
       uint32_t chunk_ctr = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++tile) {
+        if ((tile & 1) != (uint32_t)g) continue;
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
-        const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+        const uint32_t aphase = my_tiles & 1;
+        ++my_tiles;
+        const int m = mb * 128 + row;
+        const bool has_res = (p.residual != nullptr) && (m < p.M);
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        const int m = mb * 128 + row;
         for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
           const int n0 = nb0 * BLOCK_N + c * CH_ELEMS;
           if (n0 >= p.N) break;  // uniform across the CTA
           const uint32_t buf = chunk_ctr & 1;
+          // residual: this thread's 128 contiguous bytes of its row, issued first so the latency overlaps the TMEM read
+          uint4 rv[8];
+          if (has_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.residual) + (size_t)m * p.N + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
+          }
           // the TMA store that last read this staging buffer must have finished reading it
-          if (threadIdx.x == 128) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          const uint32_t st_row = sEpi + buf * 16384 + row * 128;
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(bar_id, 128);
+          const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
 #pragma unroll
           for (int h = 0; h < CH_ELEMS / 32; ++h) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, r);
             tmem_ld_wait();
             float v[32];
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + h * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + h * 32 + j;
-              float x = __uint_as_float(r[j]);
-              if (p.bias != nullptr && n < p.N) x += __ldg(p.bias + n);
-              v[j] = x;
+              for (int q = 0; q < 8; ++q) {
+                const float4 bb = __ldg(b4 + q);
+                v[4 * q] = __uint_as_float(r[4 * q]) + bb.x;
+                v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+                v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z;
+                v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             }
-            if (p.residual != nullptr && m < p.M) {
-              const T* rp = reinterpret_cast<const T*>(p.residual) + (size_t)m * p.N + n0 + h * 32;
+            if (has_res) {
+              if constexpr (sizeof(T) == 4) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + h * 32 + j < p.N) v[j] += (float)rp[j];
+                for (int q = 0; q < 8; ++q) {
+                  v[4 * q] += __uint_as_float(rv[q].x);
+                  v[4 * q + 1] += __uint_as_float(rv[q].y);
+                  v[4 * q + 2] += __uint_as_float(rv[q].z);
+                  v[4 * q + 3] += __uint_as_float(rv[q].w);
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 t = rv[h * 4 + q];
+                  const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[8 * q + 2 * e] += __uint_as_float(w4[e] << 16);
+                    v[8 * q + 2 * e + 1] += __uint_as_float(w4[e] & 0xFFFF0000u);
+                  }
+                }
+              }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -288,9 +328,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (threadIdx.x == 128) {
-            tma_store_2d(&tmD, sEpi + buf * 16384, n0, mb * 128);
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            tma_store_2d(&tmD, sEpi + (g * 2 + buf) * 16384, n0, mb * 128);
             tma_store_commit();
           }
         }
@@ -299,25 +339,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      if (threadIdx.x == 128) tma_store_wait_all();
+      if (leader) tma_store_wait_all();
     } else {
       // ---------------------------------------------------------------- EPI_KNN
-      float* s_gn = reinterpret_cast<float*>(sEpi_gen);  // [2][BLOCK_N]
+      float* gn = reinterpret_cast<float*>(sEpi_gen) + g * BLOCK_N;  // this warpgroup's gallery-norm slice
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         float b1 = INFINITY, b2 = INFINITY;
         int i1 = -1, i2 = -1;
         for (int nb = nb0; nb < nb0 + nbn; ++nb, ++tile) {
-          const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
-          float* gn = s_gn + as * BLOCK_N;
-          // stage the gallery norms of this n-block (previous user of this buffer finished two tiles ago; the
-          // barrier below also orders it against the other warps' reads of the other buffer)
+          if ((tile & 1) != (uint32_t)g) continue;
+          const uint32_t aphase = my_tiles & 1;
+          ++my_tiles;
+          named_bar_sync(bar_id, 128);  // everyone is done reading the previous tile's norms
           for (int j = row; j < BLOCK_N; j += 128) {
             const int n = nb * BLOCK_N + j;
             gn[j] = (n < p.N) ? __ldg(p.gnorm + n) : INFINITY;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           mbar_wait(tfull_bar(as), aphase);
           tc_fence_after();
 #pragma unroll 1
@@ -349,8 +389,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int m = mb * 128 + row;
         if (m < p.M) {
+          // one (top-2) record per (row, gallery split, warpgroup)
           const int sp = nb0 / p.n_blocks_per_unit;
-          const size_t o = ((size_t)m * p.splits + sp) * 2;
+          const size_t o = (((size_t)m * p.splits + sp) * 2 + g) * 2;
           p.part_score[o] = b1;
           p.part_score[o + 1] = b2;
           p.part_idx[o] = i1;

@@ -496,7 +496,7 @@ __global__ void knn_finalize_kernel(const float* __restrict__ q, const float* __
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nq) return;
-  const int ncand = splits * 2;
+  const int ncand = splits * 4;  // per split: 2 epilogue warpgroups x top-2
   // each lane keeps its own KEEP best, then the warp extracts the global KEEP best one at a time
   float ls[KEEP];
   int li[KEEP];

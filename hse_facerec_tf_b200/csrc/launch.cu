@@ -162,7 +162,7 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
   }
   int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
   if (grid < 1) return;
-  kern<<<grid, 256, SM::kTotal, s>>>(tA, tB, tD, p);
+  kern<<<grid, 384, SM::kTotal, s>>>(tA, tB, tD, p);
   HFR_LAUNCH_CHECK("gemm_tc");
 }
 
@@ -202,7 +202,7 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
     return;
   }
   const int es = (int)elt_size(prec);
-  if ((a.K * es) % 16 || (a.N * es) % 16) throw Error(-1, "gemm: K and N rows must be multiples of 16 bytes");
+  if ((a.K * es) % 16 || (a.N * es) % 128) throw Error(-1, "gemm: K rows must be multiples of 16 bytes, N rows of 128 bytes");
   if (a.M >= (1ll << 31)) throw Error(-1, "gemm: M too large");
   GemmParams p;
   memset(&p, 0, sizeof(p));

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hfr_op_dwconv3x3": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "hfr_op_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "hfr_op_stem_conv": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
+    "hfr_op_stem_conv_tc": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "hfr_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_maxpool": (_i, [_vp, _vp] + [_i] * 13 + [_vp]),
 }

@@ -3,6 +3,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -53,6 +54,50 @@ static float f32_to_tf32(float f) {  // round to nearest even on the 13 dropped 
   float r;
   memcpy(&r, &u, 4);
   return r;
+}
+
+// Stem weights for the tensor-core path (see stem_s2d_kernel): [ka*kb taps][cout][16] bf16.  The colour flip, the
+// input scale and the mean subtraction of the reference's pre-processing are folded in: data channels carry scale*W for
+// the raw channel order, channels 12..14 carry -sum(mean*W) split into three bf16 terms (fp32-accurate constant).
+struct StemTcGeom { int ka, kb, pt2, pl2; };
+static std::vector<uint16_t> stem_tc_weights(const std::vector<float>& w, int kh, int kw, int cout, int pad_t, int pad_l,
+                                             int flip, float scale, const float mean[3], StemTcGeom* g) {
+  const int shy = pad_t & 1, shx = pad_l & 1;
+  g->pt2 = pad_t + shy;
+  g->pl2 = pad_l + shx;
+  g->ka = (kh + shy + 1) / 2;
+  g->kb = (kw + shx + 1) / 2;
+  std::vector<uint16_t> out((size_t)g->ka * g->kb * cout * 16, 0);
+  for (int a = 0; a < g->ka; ++a)
+    for (int b = 0; b < g->kb; ++b)
+      for (int co = 0; co < cout; ++co) {
+        uint16_t* dst = &out[(((size_t)a * g->kb + b) * cout + co) * 16];
+        double cst = 0.0;
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx) {
+            const int r = 2 * a + dy - shy, q = 2 * b + dx - shx;
+            if (r < 0 || r >= kh || q < 0 || q >= kw) continue;
+            for (int j = 0; j < 3; ++j) {
+              const int c = flip ? 2 - j : j;
+              const float ww = w[(((size_t)r * kw + q) * 3 + c) * cout + co];
+              dst[(dy * 2 + dx) * 3 + j] = f32_to_bf16(scale * ww);
+              cst -= (double)mean[c] * ww;
+            }
+          }
+        auto bf2f = [](uint16_t h) {
+          uint32_t u = (uint32_t)h << 16;
+          float f;
+          memcpy(&f, &u, 4);
+          return f;
+        };
+        const uint16_t hi = f32_to_bf16((float)cst);
+        const uint16_t mid = f32_to_bf16((float)(cst - bf2f(hi)));
+        const uint16_t lo = f32_to_bf16((float)(cst - bf2f(hi) - bf2f(mid)));
+        dst[12] = hi;
+        dst[13] = mid;
+        dst[14] = lo;
+      }
+  return out;
 }
 
 struct DevBuf {
@@ -106,6 +151,7 @@ struct hfr_model {
   std::vector<size_t> val_off, val_bytes;
   size_t per_image_bytes = 0;
   bool keep_all = false;
+  bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -114,6 +160,9 @@ struct hfr_model {
   std::vector<cudaEvent_t> ev;           // 2 per layer, re-used every step
   std::vector<double> layer_ms;
   int timed_steps = 0;
+  // tensor-core stem: staged space-to-depth input + per-preprocessing-flags weights
+  DevBuf stem_scratch;
+  std::map<int, std::pair<void*, StemTcGeom>> stem_w2;
   // host-buffer path staging
   DevBuf stage_in;
   std::vector<std::unique_ptr<DevBuf>> stage_out;
@@ -121,6 +170,7 @@ struct hfr_model {
   ~hfr_model() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto e : ev) cudaEventDestroy(e);
+    for (auto& kv : stem_w2) cudaFree(kv.second.first);
     for (auto& d : dev) {
       if (d.w) cudaFree(d.w);
       if (d.bias) cudaFree(d.bias);
@@ -248,7 +298,31 @@ struct hfr_model {
             if (flags & HFR_FLAG_SCALE_PM1) { a.scale = 1.f / 127.5f; a.mean[0] = a.mean[1] = a.mean[2] = 1.f; }
           }
           a.act = act; a.round_tf32 = round_out;
-          launch_stem(a, prec, s);
+          const bool tc = prec == HFR_BF16 && a.in_u8 && L.stride == 2 && L.dil == 1 && (L.H % 2 == 0) &&
+                          (L.W % 2 == 0) && (L.cout == 32 || L.cout == 64) && !stem_force_direct;
+          if (!tc) {
+            launch_stem(a, prec, s);
+            break;
+          }
+          const int key = flags & (HFR_FLAG_BGR | HFR_FLAG_MEAN_IMAGENET | HFR_FLAG_MEAN_VGGFACE2 | HFR_FLAG_SCALE_PM1);
+          auto it = stem_w2.find(key);
+          if (it == stem_w2.end()) {
+            StemTcGeom g;
+            std::vector<uint16_t> h = stem_tc_weights(L.w, L.kh, L.kw, L.cout, L.pad_t, L.pad_l, a.flip, a.scale, a.mean, &g);
+            it = stem_w2.emplace(key, std::make_pair(upload(h.data(), h.size() * 2), g)).first;
+          }
+          const StemTcGeom& g = it->second.second;
+          StemTcArgs t;
+          t.x = (const uint8_t*)in; t.w2 = it->second.first; t.bias = d.bias; t.y = out;
+          t.B = batch; t.H = L.H; t.W = L.W; t.Ho = L.Ho; t.Wo = L.Wo; t.cout = L.cout;
+          t.ka = g.ka; t.kb = g.kb; t.pt2 = g.pt2; t.pl2 = g.pl2; t.act = act;
+          const size_t need = (size_t)batch * (L.Ho + g.ka - 1) * (L.Wo + g.kb - 1) * 32;
+          if (need > stem_scratch.bytes) {
+            cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // previous users of the old buffer
+            stem_scratch.ensure(need);
+          }
+          t.scratch = stem_scratch.p;
+          launch_stem_tc(t, device, s);
           break;
         }
         case L_DW: {
@@ -709,6 +783,38 @@ int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* b
     }
     a.act = act;
     launch_stem(a, dtype, (cudaStream_t)stream);
+  });
+}
+
+int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias, void* y, int batch, int h, int w_,
+                        int kh, int kw, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act, int device,
+                        void* stream) {
+  return guarded([&] {
+    use_device(device);
+    int flip = (flags & HFR_FLAG_BGR) ? 1 : 0;
+    float scale = 1.f, mean[3] = {0.f, 0.f, 0.f};
+    if (flags & HFR_FLAG_MEAN_IMAGENET) { mean[0] = 103.939f; mean[1] = 116.779f; mean[2] = 123.68f; }
+    if (flags & HFR_FLAG_MEAN_VGGFACE2) { mean[0] = 91.4953f; mean[1] = 103.8827f; mean[2] = 131.0912f; }
+    if (flags & HFR_FLAG_SCALE_PM1) { scale = 1.f / 127.5f; mean[0] = mean[1] = mean[2] = 1.f; }
+    if ((h % 2) || (w_ % 2) || (cout != 32 && cout != 64)) throw Error(HFR_ERR_UNSUPPORTED, "tensor-core stem: even H/W, cout 32|64");
+    std::vector<float> wv(w_host, w_host + (size_t)kh * kw * 3 * cout);
+    StemTcGeom g;
+    std::vector<uint16_t> w2 = stem_tc_weights(wv, kh, kw, cout, pad_t, pad_l, flip, scale, mean, &g);
+    DevBuf scratch;
+    scratch.ensure((size_t)batch * (ho + g.ka - 1) * (wo + g.kb - 1) * 32);
+    void* w2d = upload(w2.data(), w2.size() * 2);
+    StemTcArgs t;
+    t.x = (const uint8_t*)x_u8; t.scratch = scratch.p; t.w2 = w2d; t.bias = bias; t.y = y;
+    t.B = batch; t.H = h; t.W = w_; t.Ho = ho; t.Wo = wo; t.cout = cout;
+    t.ka = g.ka; t.kb = g.kb; t.pt2 = g.pt2; t.pl2 = g.pl2; t.act = act;
+    try {
+      launch_stem_tc(t, device, (cudaStream_t)stream);
+      cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+    } catch (...) {
+      cudaFree(w2d);
+      throw;
+    }
+    cudaFree(w2d);
   });
 }
 

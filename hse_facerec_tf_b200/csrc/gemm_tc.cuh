@@ -21,7 +21,7 @@ namespace hfr {
 
 enum { EPI_STORE = 0, EPI_KNN = 1 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };
-enum { AMODE_2D = 0, AMODE_IM2COL = 1 };
+enum { AMODE_2D = 0, AMODE_IM2COL = 1, AMODE_STEM16 = 2 };
 
 struct GemmParams {
   int M, N, K;            // K in elements
@@ -43,6 +43,9 @@ struct GemmParams {
   int conv_kw, conv_cblocks;   // taps along W, channel blocks (of BK elements) per tap
   int conv_wo, conv_ho;        // output width/height: m -> (n, ho, wo)
   int conv_stride, conv_pad_w, conv_pad_h, conv_dil;
+  // AMODE_STEM16 (stem convolution after space-to-depth: 16 channels = 32 bytes per pixel, one MMA K-step per tap):
+  // k-block = 4 taps; taps are (a, b) over a conv_kh x conv_kw window, stride 1, no padding.  B = [taps][N][16].
+  int conv_kh, conv_taps;
 };
 
 template <typename T>
@@ -120,7 +123,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = (AMODE == AMODE_IM2COL) ? p.conv_kw * p.conv_kw * p.conv_cblocks : (p.K + BK - 1) / BK;
+  const int num_kb = (AMODE == AMODE_IM2COL)  ? p.conv_kw * p.conv_kw * p.conv_cblocks
+                     : (AMODE == AMODE_STEM16) ? (p.conv_taps + 3) / 4
+                                               : (p.K + BK - 1) / BK;
   const int units_n = (p.num_n_blocks + p.n_blocks_per_unit - 1) / p.n_blocks_per_unit;
 
   // unit -> (m block, first n block, n block count).  STORE: n fastest (neighbouring CTAs share the A tile in L2).
@@ -147,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         int im_n = 0, im_h = 0, im_w = 0;
-        if (AMODE == AMODE_IM2COL) {
+        if (AMODE != AMODE_2D) {
           int m0 = mb * 128;
           im_w = m0 % p.conv_wo;
           int t = m0 / p.conv_wo;
@@ -165,10 +170,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
                                  im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
                                  (uint16_t)(s * p.conv_dil), (uint16_t)(r * p.conv_dil));
+            } else if (AMODE == AMODE_STEM16) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                int tap = kb * 4 + t;
+                if (tap >= p.conv_taps) tap = 0;  // padding tap: its weights are zero (OOB in B's tap dimension)
+                const int a = tap / p.conv_kw, b = tap - a * p.conv_kw;
+                tma_load_im2col_4d(sA + stage * SM::kABytes + t * 4096, &tmA, full_bar(stage), 0, im_w, im_h, im_n,
+                                   (uint16_t)b, (uint16_t)a);
+              }
             } else {
               tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
             }
-            tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
+            if (AMODE == AMODE_STEM16)
+              tma_load_3d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), 0, nb * BLOCK_N, kb * 4);
+            else
+              tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -195,11 +212,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(sA + stage * SM::kABytes);
-            const uint64_t bdesc = umma_desc_sw128(sB + stage * SM::kBBytes);
+            if constexpr (AMODE == AMODE_STEM16) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte swizzle row
-              umma<TR::kTF32>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {  // one tap (16 channels = 32 bytes = one K-step) per MMA
+                const uint64_t adesc = umma_desc_sw32(sA + stage * SM::kABytes + k * 4096);
+                const uint64_t bdesc = umma_desc_sw32(sB + stage * SM::kBBytes + k * (BLOCK_N * 32));
+                umma<TR::kTF32>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+              }
+            } else {
+              const uint64_t adesc = umma_desc_sw128(sA + stage * SM::kABytes);
+              const uint64_t bdesc = umma_desc_sw128(sB + stage * SM::kBBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte swizzle row
+                umma<TR::kTF32>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+              }
             }
             umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
             if (++stage == STAGES) {
@@ -258,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, r);
             tmem_ld_wait();
             float v[32];
-            if (p.bias != nullptr) {
+            if (p.bias != nullptr && n0 + h * 32 < p.N) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + h * 32);
 #pragma unroll
               for (int q = 0; q < 8; ++q) {

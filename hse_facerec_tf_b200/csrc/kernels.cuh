@@ -123,6 +123,47 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Stem on the tensor cores, step 1: space-to-depth staging of the uint8 image for a stride-2 KHxKW convolution.
+//   S[b, Y, X, (dy*2+dx)*3 + j] = u8[b, 2Y+dy-pt, 2X+dx-pl, j]   (0 outside the image)      j = raw channel 0..2
+//   S[b, Y, X, 12..15]          = 1 inside the image, 0 in the padding ("valid" channels: they carry the folded
+//                                 -mean term, so mean subtraction stays exact and padding stays exactly zero)
+// pt/pl are even and H/W are even, so a 2x2 block is entirely inside or entirely outside the image.  uint8 values are
+// exact in bf16.  The stride-2 conv then is a stride-1 (KH'/2)x(KW'/2) conv over S: 16 channels = one MMA K-step.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ s,
+                                                       int B, int H, int W, int Hs, int Ws, int pt, int pl) {
+  const long long total = (long long)B * Hs * Ws;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Ws);
+    const int Y = (int)((i / Ws) % Hs);
+    const int b = (int)(i / ((long long)Ws * Hs));
+    const int iy = 2 * Y - pt, ix = 2 * X - pl;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    if (iy >= 0 && iy + 1 < H && ix >= 0 && ix + 1 < W) {
+      const uint8_t* p0 = x + (((size_t)b * H + iy) * W + ix) * 3;
+      const uint8_t* p1 = p0 + (size_t)W * 3;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        v[e] = (float)p0[e];
+        v[6 + e] = (float)p1[e];
+      }
+      v[12] = v[13] = v[14] = v[15] = 1.f;
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(s + (size_t)i * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Depthwise 3x3 (+ per-channel scale folded into the taps, bias, ReLU6), stride 1 or 2, TF SAME/explicit padding.
 // HBM-bound: every input byte is fetched once by TMA into a shared-memory halo tile (out-of-range coordinates are
 // zero-filled by the TMA unit, which is exactly the zero padding), every output byte is written once as 16-byte

@@ -46,6 +46,13 @@ void use_device(int device) {
   device_sm_count(device);
 }
 
+static unsigned grid_for(long long total, int threads, long long cap = 148LL * 32) {
+  long long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
 // ---------------------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -257,13 +264,54 @@ void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s) {
     launch_gemm_store<float, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s);
 }
 
-// ---------------------------------------------------------------------------------------------- simple kernels
-static unsigned grid_for(long long total, int threads, long long cap = 148LL * 32) {
-  long long g = (total + threads - 1) / threads;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (unsigned)g;
+// ---------------------------------------------------------------------------------------------- tensor-core stem
+void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
+  static PFN_encodeIm2col enc = (PFN_encodeIm2col)driver_fn("cuTensorMapEncodeIm2col");
+  if (a.cout > 64 || a.cout % 32) throw Error(-5, "tensor-core stem: cout must be 32 or 64");
+  const int Hs = a.Ho + a.ka - 1, Ws = a.Wo + a.kb - 1;
+  {
+    const long long total = (long long)a.B * Hs * Ws;
+    stem_s2d_kernel<<<grid_for(total, 256), 256, 0, s>>>(a.x, (__nv_bfloat16*)a.scratch, a.B, a.H, a.W, Hs, Ws, a.pt2,
+                                                          a.pl2);
+    HFR_LAUNCH_CHECK("stem_s2d");
+  }
+  const int64_t M = (int64_t)a.B * a.Ho * a.Wo;
+  const uint64_t dims[4] = {16, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)a.B};
+  const uint64_t strides[3] = {32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32};
+  int lower[2] = {0, 0};
+  int upper[2] = {-(a.kb - 1), -(a.ka - 1)};
+  uint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tA;
+  CUresult r = enc(&tA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.scratch, (const cuuint64_t*)dims,
+                   (const cuuint64_t*)strides, lower, upper, 16, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-6, "cuTensorMapEncodeIm2col(stem) failed with CUresult " + std::to_string((int)r));
+  {
+    int drv = 0;
+    cuda_check(cudaDriverGetVersion(&drv), "cudaDriverGetVersion");
+    if (drv <= 13010 && (uint64_t)a.B * Hs * Ws * 32 < 131072) reinterpret_cast<uint64_t*>(&tA)[1] &= ~(1ull << 21);
+  }
+  // weights [taps][cout][16]: 3-D map, box {16, 64, 4} (rows >= cout and taps >= ka*kb are zero-filled)
+  const int taps = a.ka * a.kb;
+  const uint64_t wd[3] = {16, (uint64_t)a.cout, (uint64_t)taps};
+  const uint64_t ws[2] = {32, (uint64_t)a.cout * 32};
+  const uint32_t wbox[3] = {16, 64, 4};
+  CUtensorMap tB = make_tiled(a.w2, PREC_BF16, 3, wd, ws, wbox, CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tD = make_tmap_2d(a.y, PREC_BF16, (uint64_t)M, (uint64_t)a.cout, 128);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = a.cout; p.K = taps * 16;
+  p.bias = a.bias; p.act = a.act;
+  p.conv_kw = a.kb; p.conv_kh = a.ka; p.conv_taps = taps; p.conv_wo = a.Wo; p.conv_ho = a.Ho;
+  p.conv_stride = 1; p.conv_dil = 1;
+  p.num_m_blocks = (int)((M + 127) / 128);
+  p.num_n_blocks = 1;
+  p.n_blocks_per_unit = 1;
+  p.num_units = p.num_m_blocks;
+  launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, p, device, s);
 }
+
+// ---------------------------------------------------------------------------------------------- simple kernels
 
 void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s) {
   PoolParams p;

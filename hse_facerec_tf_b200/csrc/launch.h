@@ -35,6 +35,18 @@ struct StemArgs {
 };
 void launch_stem(const StemArgs& a, int prec, cudaStream_t s);
 
+// Stem on the tensor cores (bf16, uint8 input, stride 2, even H/W): space-to-depth staging + STEM16 implicit GEMM.
+struct StemTcArgs {
+  const uint8_t* x;     // [B,H,W,3]
+  void* scratch;        // [B,Hs,Ws,16] bf16, Hs = Ho + ka - 1, Ws = Wo + kb - 1
+  const void* w2;       // [ka*kb][cout][16] bf16 (built by stem_tc_weights)
+  const float* bias;    // [cout] or null
+  void* y;              // [B,Ho,Wo,cout] bf16
+  int B, H, W, Ho, Wo, cout, ka, kb, pt2, pl2;   // pt2/pl2: even padding used by the staging kernel
+  int act;
+};
+void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s);
+
 struct DwArgs {
   const void* x;      // [B,H,W,C] of T
   const float* w;     // [9][C]

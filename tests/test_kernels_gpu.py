@@ -134,6 +134,54 @@ def test_stem_conv(prec, case):
     assert (got - ref).abs().max().item() <= (4e-2 if prec == 2 else 2e-3)
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 3, 32, 0), (3, 64, 48, 7, 64, 3), (2, 192, 192, 3, 32, 0), (1, 224, 224, 7, 64, 3),
+                                  (2, 20, 20, 5, 64, 2), (2, 16, 16, 3, 64, 1)])
+@pytest.mark.parametrize("flags", [_lib.FLAG_BGR | _lib.FLAG_MEAN_IMAGENET, _lib.FLAG_BGR | _lib.FLAG_MEAN_VGGFACE2,
+                                   _lib.FLAG_SCALE_PM1])
+def test_stem_conv_tensor_core(case, flags):
+    """space-to-depth + STEM16 implicit GEMM vs the fp32 convolution of the pre-processed image.  The image enters
+    exactly (uint8 in bf16), the mean term is exact; only the weights are rounded to bf16."""
+    B, H, W, k, cout, pad = case
+    g = torch.Generator(device="cpu").manual_seed(H + k + cout)
+    w = (torch.randn(k, k, 3, cout, generator=g) * (0.5 / k)).float()
+    if flags & _lib.FLAG_SCALE_PM1:
+        w = w * 60
+    else:
+        w = w / 60
+    bias = torch.randn(cout, generator=g).to(DEV)
+    x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(DEV)
+    ho = (H + 2 * pad - k) // 2 + 1 if pad else -(-H // 2)
+    wo = (W + 2 * pad - k) // 2 + 1 if pad else -(-W // 2)
+    if pad:
+        pt = pl = pad
+        pb, pr = (ho - 1) * 2 + k - H - pt, (wo - 1) * 2 + k - W - pl
+    else:   # TF SAME
+        th, tw = max((ho - 1) * 2 + k - H, 0), max((wo - 1) * 2 + k - W, 0)
+        pt, pl, pb, pr = th // 2, tw // 2, th - th // 2, tw - tw // 2
+    y = torch.full((B, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wc = w.contiguous()
+    check(lib.hfr_op_stem_conv_tc(x.data_ptr(), wc.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, k, k, pt, pl, ho, wo,
+                                  cout, flags, 2, 0, _stream()))
+    # reference = what the kernel is specified to compute: sum(u8 * bf16(scale * W)) - sum_valid(mean * W) + bias
+    if flags & _lib.FLAG_SCALE_PM1:
+        xs, scale, mean = x.double(), 1.0 / 127.5, [1.0, 1.0, 1.0]
+    else:
+        xs, scale = x.double().flip(-1), 1.0
+        mean = [103.939, 116.779, 123.68] if flags & _lib.FLAG_MEAN_IMAGENET else [91.4953, 103.8827, 131.0912]
+    wd = w.to(DEV)
+    wq = (wd * scale).bfloat16().double()
+    pads = (pl, max(pr, 0), pt, max(pb, 0))
+    xp = F.pad(xs.permute(0, 3, 1, 2), pads)
+    mp = F.pad(torch.ones_like(xs).permute(0, 3, 1, 2) * torch.tensor(mean, device=DEV, dtype=torch.float64).view(1, 3, 1, 1), pads)
+    ref = F.conv2d(xp, wq.permute(3, 2, 0, 1), bias.double(), stride=2) - F.conv2d(mp, wd.double().permute(3, 2, 0, 1), None, stride=2)
+    ref = torch.clamp(ref, 0, 6).permute(0, 2, 3, 1)[:, :ho, :wo]
+    got = y.double()
+    assert torch.isfinite(got).all()
+    # weights are compared at their bf16 values, so what is left is the bf16 rounding of the output (<= 2^-8 * 6)
+    # and of the scaled weights in the x/127.5-1 mode
+    assert (got - ref).abs().max().item() <= 0.05
+
+
 # ------------------------------------------------------------------------------------------------ KxK conv / pool
 CONV_CASES = [  # (B, H, W, cin, cout, k, stride)
     (2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1), (5, 7, 7, 512, 512, 3, 1),

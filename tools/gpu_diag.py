@@ -112,6 +112,38 @@ def diag_conv():
                       " got[0,1,:4,0]", got[0, 1, :4, 0].tolist(), "ref", ref[0, 1, :4, 0].tolist())
 
 
+def diag_stem():
+    for (B, H, W, k, cout, pad) in [(1, 16, 16, 3, 32, 0), (1, 16, 16, 3, 64, 0), (2, 32, 32, 7, 64, 3), (1, 224, 224, 7, 64, 3)]:
+        g = torch.Generator().manual_seed(5)
+        x = torch.randint(0, 4, (B, H, W, 3), generator=g, dtype=torch.uint8).to(DEV)
+        w = torch.randint(-1, 2, (k, k, 3, cout), generator=g).float().contiguous()
+        ho = (H + 2 * pad - k) // 2 + 1 if pad else H // 2
+        wo = (W + 2 * pad - k) // 2 + 1 if pad else W // 2
+        if pad:
+            pt = pl = pad
+            pb, pr = (ho - 1) * 2 + k - H - pt, (wo - 1) * 2 + k - W - pl
+        else:
+            th, tw = max((ho - 1) * 2 + k - H, 0), max((wo - 1) * 2 + k - W, 0)
+            pt, pl, pb, pr = th // 2, tw // 2, th - th // 2, tw - tw // 2
+        y = torch.full((B, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        rc = lib.hfr_op_stem_conv_tc(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), B, H, W, k, k, pt, pl, ho, wo, cout, 0, 0, 0, None)
+        torch.cuda.synchronize()
+        if rc:
+            print(f"stem {B}x{H}x{W} k{k} ->{cout}: rc={rc} {lib.hfr_last_error().decode()}")
+            continue
+        xp = F.pad(x.float().permute(0, 3, 1, 2), (pl, max(pr, 0), pt, max(pb, 0)))
+        ref = F.conv2d(xp, w.to(DEV).permute(3, 2, 0, 1), None, stride=2).permute(0, 2, 3, 1)[:, :ho, :wo]
+        got = torch.nan_to_num(y.float(), nan=1e9)
+        bad = (got - ref).abs() > 0.01 * ref.abs() + 0.01
+        print(f"stem {B}x{H}x{W} k{k} ->{cout}: mismatches={bad.sum().item()}/{bad.numel()}")
+        if bad.any():
+            print("   first bad (b,y,x,c):", bad.nonzero()[:6].tolist())
+            print("   bad per out row (img0):", bad[0].sum(dim=(1, 2)).tolist(), " per col:", bad[0].sum(dim=(0, 2)).tolist(),
+                  " per channel:", bad[0].sum(dim=(0, 1)).tolist())
+            print("   got[0,0,:4,0]", got[0, 0, :4, 0].tolist(), "ref", ref[0, 0, :4, 0].tolist())
+            print("   got[0,1,:4,1]", got[0, 1, :4, 1].tolist(), "ref", ref[0, 1, :4, 1].tolist())
+
+
 def diag_knn():
     import hse_facerec_tf_b200 as hfr
     for prec in ("bf16", "tf32"):
@@ -158,6 +190,6 @@ if __name__ == "__main__":
     for w in what:
         print(f"===== {w}")
         try:
-            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv}[w]()
+            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv, "stem": diag_stem}[w]()
         except Exception:
             traceback.print_exc()

@@ -12,6 +12,7 @@ from .extractor import FeatureExtractor, TensorFlowInference, extract_keras_feat
 from .age_gender import FacialImageProcessing  # noqa: F401
 from .classifier import KNeighborsClassifier  # noqa: F401
 from .preprocessing import normalize  # noqa: F401
+from . import parallel  # noqa: F401
 
 
 def launch_count() -> int:

@@ -72,14 +72,8 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         self.n_features_in_ = int(g.shape[1] - self._pad)
         offset = 0
         if self.sharded:
-            import torch.distributed as dist
-            world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
-            counts = [None] * world
-            dist.all_gather_object(counts, int(g.shape[0]), group=self.process_group)
-            labels = [None] * world
-            dist.all_gather_object(labels, y, group=self.process_group)
-            offset = int(sum(counts[:rank]))
-            y = np.concatenate(labels)
+            from .parallel import shard_layout
+            offset, y, _ = shard_layout(g.shape[0], y, self.process_group)
         self.classes_, self._y = np.unique(y, return_inverse=True)
         self._labels = y
         self._gallery = g  # keeps the fp32 rows alive: the kernel re-ranks its candidates against them
@@ -109,14 +103,10 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         stream = _stream_ptr(q.device)
         check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, d2.data_ptr(), idx.data_ptr(), stream))
         if self.sharded:
-            import torch.distributed as dist
-            world = dist.get_world_size(self.process_group)
-            d_all = torch.empty(world * nq, dtype=torch.float32, device=q.device)
-            i_all = torch.empty(world * nq, dtype=torch.int64, device=q.device)
-            dist.all_gather_into_tensor(d_all, d2, group=self.process_group)
-            dist.all_gather_into_tensor(i_all, idx, group=self.process_group)
-            check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), world, nq, d2.data_ptr(), idx.data_ptr(), dev,
-                                    stream))
+            from .parallel import gather_pairs
+            d_all, i_all = gather_pairs(d2, idx, self.process_group)
+            check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), d_all.shape[0], nq, d2.data_ptr(), idx.data_ptr(),
+                                    dev, stream))
         self._last_idx = idx
         ind = idx.cpu().numpy().reshape(-1, 1)
         if return_distance:

@@ -81,3 +81,17 @@ def cosine(a, b):
     a = a.astype(np.float64)
     b = b.astype(np.float64)
     return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1) + 1e-30)
+
+
+def merge_pairs_reference(d_all: np.ndarray, i_all: np.ndarray):
+    """Test oracle for hfr_knn_merge: per query the smallest distance over the shards, ties -> lowest global index."""
+    P, nq = d_all.shape
+    best_d = np.full(nq, np.inf, np.float32)
+    best_i = np.full(nq, -1, np.int64)
+    for p in range(P):
+        for q in range(nq):
+            if i_all[p, q] < 0:
+                continue
+            if best_i[q] < 0 or d_all[p, q] < best_d[q] or (d_all[p, q] == best_d[q] and i_all[p, q] < best_i[q]):
+                best_d[q], best_i[q] = d_all[p, q], i_all[p, q]
+    return best_d, best_i

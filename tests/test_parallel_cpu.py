@@ -1,0 +1,84 @@
+"""N>1 host logic on CPU: two gloo processes shard a gallery, score their shard with the oracle (scikit-learn), exchange
+(distance, index) pairs through hse_facerec_tf_b200.parallel and must reproduce the single-gallery 1-NN result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from sklearn import neighbors
+
+from hse_facerec_tf_b200 import parallel
+from tests.helpers import merge_pairs_reference
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    rs = np.random.RandomState(0)
+    g = rs.randn(1001, 32).astype(np.float32)
+    g[700] = g[3]                        # duplicate rows across the shard boundary: tie -> lowest global index
+    q = np.concatenate([g[[3, 500, 1000]], rs.randn(40, 32).astype(np.float32)])
+    y = (np.arange(1001) * 7) % 113
+    return g, q, y
+
+
+def _worker(rank, ws, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        g, q, y = _problem()
+        a, b = parallel.shard_rows(len(g), ws, rank)
+        offset, labels, counts = parallel.shard_layout(b - a, y[a:b])
+        assert offset == a and counts == [parallel.shard_rows(len(g), ws, r)[1] - parallel.shard_rows(len(g), ws, r)[0]
+                                          for r in range(ws)]
+        np.testing.assert_array_equal(labels, y)
+        nn = neighbors.NearestNeighbors(n_neighbors=1, algorithm="brute").fit(g[a:b])
+        d, i = nn.kneighbors(q)
+        d2 = torch.from_numpy((d[:, 0] ** 2).astype(np.float32))
+        gi = torch.from_numpy(i[:, 0].astype(np.int64) + offset)
+        d_all, i_all = parallel.gather_pairs(d2, gi)
+        assert d_all.shape == (ws, len(q))
+        _, best = merge_pairs_reference(d_all.numpy(), i_all.numpy())
+        emb = parallel.gather_rows(torch.from_numpy(g[a:b]))          # embeddings all-gather with ragged blocks
+        assert torch.equal(emb, torch.from_numpy(g))
+        mine = parallel.split_batch(np.arange(10))
+        assert list(mine) == list(range(*parallel.shard_rows(10, ws, rank)))
+        if rank == 0:
+            out.put(best)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gallery_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    best = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g, q, y = _problem()
+    ref = neighbors.KNeighborsClassifier(n_neighbors=1, p=2).fit(g, y)
+    ref_i = ref.kneighbors(q, return_distance=False)[:, 0]
+    assert best[0] == 3                      # duplicate of row 3 lives in shard 1 as row 700: lowest index wins
+    np.testing.assert_array_equal(best[1:], ref_i[1:])
+    np.testing.assert_array_equal(y[best], ref.predict(q))
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 1000, 1001):
+        for ws in (1, 2, 3, 8):
+            blocks = [parallel.shard_rows(n, ws, r) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1

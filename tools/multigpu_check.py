@@ -1,0 +1,54 @@
+"""Run under torchrun with >= 2 GPUs: the sharded paths must reproduce the single-GPU results.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hse_facerec_tf_b200 as hfr  # noqa: E402
+from hse_facerec_tf_b200 import parallel  # noqa: E402
+
+
+def main():
+    rank, ws, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    rs = np.random.RandomState(0)
+    # ---- 1-NN: gallery row-sharded, NCCL all-gather of (d2, idx), merge kernel
+    n, nq, d = 50_001, 777, 1024
+    g = rs.randn(n, d).astype(np.float32)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    g[40_000] = g[5]                                       # duplicate across shards
+    q = g[rs.randint(0, n, nq)] + 0.03 * rs.randn(nq, d).astype(np.float32)
+    q[0] = g[5]
+    y = np.arange(n) % 1000
+    a, b = parallel.shard_rows(n, ws, rank)
+    sharded = hfr.KNeighborsClassifier(1, 2, device=dev, precision="bf16", sharded=True).fit(g[a:b], y[a:b])
+    d_s, i_s = sharded.kneighbors(q)
+    whole = hfr.KNeighborsClassifier(1, 2, device=dev, precision="bf16").fit(g, y)
+    d_w, i_w = whole.kneighbors(q)
+    np.testing.assert_array_equal(i_s, i_w)
+    np.testing.assert_allclose(d_s, d_w, rtol=1e-6, atol=1e-7)
+    assert i_s[0, 0] == 5
+    np.testing.assert_array_equal(sharded.predict(q), whole.predict(q))
+    # ---- extraction: batch sharded, no collective on the data path; gather only to compare
+    pb = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "age_gender_quantized.pb")
+    tfi = hfr.TensorFlowInference(pb, "input_1:0", "global_pooling/Mean:0", device=dev, precision="bf16", input_hw=192)
+    x = rs.randint(0, 256, (37, 192, 192, 3)).astype(np.uint8)
+    mine = parallel.split_batch(x)
+    e_local = tfi.extract_batch(torch.from_numpy(np.ascontiguousarray(mine)).to(dev))
+    e_all = parallel.gather_rows(e_local)
+    e_ref = tfi.extract_batch(torch.from_numpy(x).to(dev))
+    assert torch.equal(e_all, e_ref), (e_all - e_ref).abs().max()
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check ok: world={ws}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

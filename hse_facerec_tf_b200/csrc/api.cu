@@ -152,6 +152,7 @@ struct hfr_model {
   size_t per_image_bytes = 0;
   bool keep_all = false;
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
+  int sub_batch = getenv("HFR_SUB_BATCH") ? atoi(getenv("HFR_SUB_BATCH")) : 0;
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -272,14 +273,32 @@ struct hfr_model {
     }
   }
 
+  // exact (unpadded) bytes of one image of value v
+  size_t value_exact_bytes(int v) const {
+    const ValueInfo& vi = plan.values[(size_t)v];
+    return (size_t)vi.H * vi.W * vi.C * (vi.is_vector ? 4 : elt_size(precision));
+  }
+
   void run_layers(const void* x, int in_dtype, int batch, int flags, void* const* outs, cudaStream_t s) {
+    // L2-sized sub-batching: every tensor is batch-major, so a slice of the batch is a pointer offset.  Running the
+    // whole layer list on one slice at a time keeps producer->consumer tensors L2-resident.
+    int sub = sub_batch > 0 && !timing ? sub_batch : batch;
+    if (sub > batch) sub = batch;
+    for (int b0 = 0; b0 < batch; b0 += sub) run_slice(x, in_dtype, batch, b0, std::min(sub, batch - b0), flags, s);
+    finish_outputs(batch, flags, outs, s);
+  }
+
+  void run_slice(const void* x_all, int in_dtype, int total, int img0, int batch, int flags, cudaStream_t s) {
     const int prec = precision;
     const int rt = (prec == HFR_TF32);
+    const size_t in_img_bytes = (size_t)plan.in_h * plan.in_w * plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);
+    const void* x = (const char*)x_all + (size_t)img0 * in_img_bytes;
+    auto vptr = [&](int v) -> void* { return (char*)val_ptr(v, total) + (size_t)img0 * value_exact_bytes(v); };
     for (size_t i = 0; i < plan.layers.size(); ++i) {
       const Layer& L = plan.layers[i];
       const LayerDev& d = dev[i];
-      const void* in = L.in == 0 ? x : val_ptr(L.in, batch);
-      void* out = val_ptr(L.out, batch);
+      const void* in = L.in == 0 ? x : vptr(L.in);
+      void* out = vptr(L.out);
       const int act = L.act;  // A_NONE/A_RELU/A_RELU6 share values with the kernels' ACT_* codes
       const int round_out = rt && feeds_tensor_core(L.out);
       if (timing) cuda_check(cudaEventRecord(ev[2 * i], s), "cudaEventRecord");
@@ -336,7 +355,7 @@ struct hfr_model {
         case L_PW: {
           GemmArgs a;
           a.a = in; a.b = d.w; a.bias = d.bias;
-          a.residual = L.in2 >= 0 ? val_ptr(L.in2, batch) : nullptr;
+          a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
           a.y = out; a.M = (int64_t)batch * L.Ho * L.Wo; a.N = L.cout; a.K = L.cin;
           a.act = act; a.round_tf32 = round_out;
           launch_gemm(a, prec, device, s);
@@ -345,7 +364,7 @@ struct hfr_model {
         case L_CONV: {
           ConvArgs a;
           a.x = in; a.w = d.w; a.bias = d.bias;
-          a.residual = L.in2 >= 0 ? val_ptr(L.in2, batch) : nullptr;
+          a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
           a.y = out; a.B = batch; a.H = L.H; a.W = L.W; a.cin = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.cout = L.cout;
           a.kh = L.kh; a.kw = L.kw; a.stride = L.stride; a.pad_t = L.pad_t; a.pad_l = L.pad_l; a.dil = L.dil;
           a.act = act; a.round_tf32 = round_out;
@@ -383,6 +402,10 @@ struct hfr_model {
       }
       ++timed_steps;
     }
+  }
+
+  void finish_outputs(int batch, int flags, void* const* outs, cudaStream_t s) {
+    const int prec = precision;
     for (size_t o = 0; o < plan.outputs.size(); ++o) {
       const int v = plan.outputs[o];
       const ValueInfo& vi = plan.values[(size_t)v];

@@ -78,7 +78,7 @@ struct GemmSmem {
 template <typename T, int BLOCK_N, int EPI, int AMODE>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using TR = GemmTraits<T>;
   using SM = GemmSmem<BLOCK_N, EPI>;
   constexpr int STAGES = SM::kStages;
@@ -99,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return sBar + 64u + 8u * s; };
   auto tfull_bar = [&](int s) { return sBar + 128u + 8u * s; };
   auto tempty_bar = [&](int s) { return sBar + 144u + 8u * s; };
+  auto rfull_bar = [&](int s) { return sBar + 160u + 8u * s; };  // residual tile landed in staging buffer s (0..3)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmD);
+    if (EPI == EPI_STORE && p.residual != nullptr) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -115,6 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 4; ++s) mbar_init(rfull_bar(s), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -253,31 +256,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int CH_ELEMS = 128 / (int)sizeof(T);  // columns per 128-byte staging chunk (32 fp32 / 64 bf16)
       constexpr int NCHUNK = BLOCK_N / CH_ELEMS;
       uint32_t chunk_ctr = 0;
+      const bool use_res = (p.residual != nullptr);
+      // Residual tiles travel by TMA into the staging buffer the output chunk will be written to (same swizzled
+      // layout, updated in place), prefetched one chunk ahead by the warpgroup leader.
+      const int units_n2 = (p.num_n_blocks + p.n_blocks_per_unit - 1) / p.n_blocks_per_unit;
+      int pf_t = g, pf_c = 0;           // leader only: next (local tile, chunk) whose residual has not been requested
+      uint32_t pf_ctr = 0;
+      auto prefetch_next = [&]() {      // leader only
+        const int u2 = blockIdx.x + pf_t * gridDim.x;
+        if (u2 >= p.num_units) return;
+        const int mb2 = u2 / units_n2, nb2 = u2 % units_n2;
+        const int n2 = nb2 * BLOCK_N + pf_c * CH_ELEMS;
+        const uint32_t b2 = pf_ctr & 1;
+        mbar_expect_tx(rfull_bar(g * 2 + b2), 16384);
+        tma_load_2d(sEpi + (g * 2 + b2) * 16384, &tmR, rfull_bar(g * 2 + b2), n2, mb2 * 128);
+        ++pf_ctr;
+        if (++pf_c == NCHUNK || nb2 * BLOCK_N + pf_c * CH_ELEMS >= p.N) {
+          pf_c = 0;
+          pf_t += 2;
+        }
+      };
+      if (use_res && leader) prefetch_next();
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++tile) {
         if ((tile & 1) != (uint32_t)g) continue;
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         const uint32_t aphase = my_tiles & 1;
         ++my_tiles;
-        const int m = mb * 128 + row;
-        const bool has_res = (p.residual != nullptr) && (m < p.M);
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
           const int n0 = nb0 * BLOCK_N + c * CH_ELEMS;
           if (n0 >= p.N) break;  // uniform across the CTA
           const uint32_t buf = chunk_ctr & 1;
-          // residual: this thread's 128 contiguous bytes of its row, issued first so the latency overlaps the TMEM read
-          uint4 rv[8];
-          if (has_res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.residual) + (size_t)m * p.N + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
-          }
-          // the TMA store that last read this staging buffer must have finished reading it
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(bar_id, 128);
           const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
+          uint4 rv[8];
+          if (use_res) {
+            if (leader) {
+              tma_store_wait_read<0>();  // the other buffer's last store has finished reading it ...
+              prefetch_next();           // ... so the next chunk's residual may land there
+            }
+            mbar_wait(rfull_bar(g * 2 + buf), (chunk_ctr >> 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t a = st_row + (((uint32_t)q ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rv[q].x), "=r"(rv[q].y), "=r"(rv[q].z), "=r"(rv[q].w)
+                           : "r"(a));
+            }
+          } else {
+            // the TMA store that last read this staging buffer must have finished reading it
+            if (leader) tma_store_wait_read<1>();
+            named_bar_sync(bar_id, 128);
+          }
 #pragma unroll
           for (int h = 0; h < CH_ELEMS / 32; ++h) {
             uint32_t r[32];
@@ -298,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             }
-            if (has_res) {
+            if (use_res) {
               if constexpr (sizeof(T) == 4) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {

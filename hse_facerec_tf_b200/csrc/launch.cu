@@ -157,8 +157,8 @@ void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------- GEMM (tcgen05)
 template <typename T, int BLOCK_N, int EPI, int AMODE>
-static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const GemmParams& p,
-                             int device, cudaStream_t s) {
+static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tR,
+                             const GemmParams& p, int device, cudaStream_t s) {
   using SM = GemmSmem<BLOCK_N, EPI>;
   auto kern = gemm_tc_kernel<T, BLOCK_N, EPI, AMODE>;
   static std::atomic<bool> configured[64];
@@ -169,7 +169,7 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
   }
   int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
   if (grid < 1) return;
-  kern<<<grid, 384, SM::kTotal, s>>>(tA, tB, tD, p);
+  kern<<<grid, 384, SM::kTotal, s>>>(tA, tB, tD, tR, p);
   HFR_LAUNCH_CHECK("gemm_tc");
 }
 
@@ -190,13 +190,14 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
   const int bn = pick_block_n(M, N, device_sm_count(device));
   CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
   CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
+  CUtensorMap tR = p.residual ? make_tmap_2d(p.residual, prec, (uint64_t)M, (uint64_t)N, 128) : tD;
   p.num_m_blocks = (int)((M + 127) / 128);
   p.num_n_blocks = (N + bn - 1) / bn;
   p.n_blocks_per_unit = 1;
   p.num_units = p.num_m_blocks * p.num_n_blocks;
-  if (bn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
-  else if (bn == 128) launch_gemm_inst<T, 128, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
-  else launch_gemm_inst<T, 64, EPI_STORE, AMODE>(tA, tB, tD, p, device, s);
+  if (bn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
+  else if (bn == 128) launch_gemm_inst<T, 128, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
+  else launch_gemm_inst<T, 64, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
 }
 
 void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
@@ -308,7 +309,7 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
   p.num_n_blocks = 1;
   p.n_blocks_per_unit = 1;
   p.num_units = p.num_m_blocks;
-  launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, p, device, s);
+  launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, tD, p, device, s);
 }
 
 // ---------------------------------------------------------------------------------------------- simple kernels
@@ -423,8 +424,8 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
   p.gnorm = a.gnorm; p.part_score = a.part_score; p.part_idx = a.part_idx;
   CUtensorMap tA = make_tmap_2d(a.q, prec, (uint64_t)a.nq, (uint64_t)a.d, 128);
   CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 256);
-  if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, p, device, s);
-  else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, p, device, s);
+  if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);
+  else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);
 }
 
 void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,

@@ -100,6 +100,27 @@ static std::vector<uint16_t> stem_tc_weights(const std::vector<float>& w, int kh
   return out;
 }
 
+// [taps][cout][16] (STEM16 layout) -> window layout [(tap*2 + plane)][64 rows][8] (rows >= cout are zero)
+static std::vector<uint16_t> stem_window_layout(const std::vector<uint16_t>& w2, int taps, int cout) {
+  std::vector<uint16_t> out((size_t)taps * 2 * 64 * 8, 0);
+  for (int t = 0; t < taps; ++t)
+    for (int co = 0; co < cout; ++co)
+      for (int c = 0; c < 16; ++c)
+        out[(((size_t)t * 2 + c / 8) * 64 + co) * 8 + c % 8] = w2[((size_t)t * cout + co) * 16 + c];
+  return out;
+}
+// conv weights [cout][taps][cin] fp32 -> window layout [(tap*planes + plane)][64 rows][8] bf16
+static std::vector<uint16_t> conv_window_layout(const float* w, int cout, int taps, int cin) {
+  const int planes = cin / 8;
+  std::vector<uint16_t> out((size_t)taps * planes * 64 * 8, 0);
+  for (int co = 0; co < cout; ++co)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < cin; ++c)
+        out[(((size_t)t * planes + c / 8) * 64 + co) * 8 + c % 8] = f32_to_bf16(w[((size_t)co * taps + t) * cin + c]);
+  return out;
+}
+static bool window_enabled() { return getenv("HFR_NO_WINDOW") == nullptr; }
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -127,6 +148,7 @@ static void* upload(const void* host, size_t bytes) {
 // ------------------------------------------------------------------------------------------------ model
 struct LayerDev {
   void* w = nullptr;      // kernel-ready weights
+  void* w_win = nullptr;  // conv_window_kernel layout, when the layer qualifies
   float* bias = nullptr;
 };
 
@@ -153,6 +175,7 @@ struct hfr_model {
   bool keep_all = false;
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
   int sub_batch = getenv("HFR_SUB_BATCH") ? atoi(getenv("HFR_SUB_BATCH")) : 0;
+  bool stem_window = window_enabled();
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -174,6 +197,7 @@ struct hfr_model {
     for (auto& kv : stem_w2) cudaFree(kv.second.first);
     for (auto& d : dev) {
       if (d.w) cudaFree(d.w);
+      if (d.w_win) cudaFree(d.w_win);
       if (d.bias) cudaFree(d.bias);
     }
   }
@@ -242,6 +266,11 @@ struct hfr_model {
       if (!L.bias.empty()) d.bias = (float*)upload(L.bias.data(), L.bias.size() * 4);
       if (L.w.empty()) continue;
       const bool gemm_operand = (L.kind == L_PW || L.kind == L_CONV);
+      if (L.kind == L_CONV && precision == HFR_BF16 && getenv("HFR_WINDOW_CONV") != nullptr && L.stride == 1 && L.dil == 1 &&
+          (L.cout == 64 || L.cout == 32) && conv_window_fits(L.cin, L.kh, L.kw)) {
+        std::vector<uint16_t> hw = conv_window_layout(L.w.data(), L.cout, L.kh * L.kw, L.cin);
+        d.w_win = upload(hw.data(), hw.size() * 2);
+      }
       if (gemm_operand && precision == HFR_BF16) {
         std::vector<uint16_t> h(L.w.size());
         for (size_t j = 0; j < h.size(); ++j) h[j] = f32_to_bf16(L.w[j]);
@@ -328,6 +357,7 @@ struct hfr_model {
           if (it == stem_w2.end()) {
             StemTcGeom g;
             std::vector<uint16_t> h = stem_tc_weights(L.w, L.kh, L.kw, L.cout, L.pad_t, L.pad_l, a.flip, a.scale, a.mean, &g);
+            if (stem_window) h = stem_window_layout(h, g.ka * g.kb, L.cout);
             it = stem_w2.emplace(key, std::make_pair(upload(h.data(), h.size() * 2), g)).first;
           }
           const StemTcGeom& g = it->second.second;
@@ -335,6 +365,7 @@ struct hfr_model {
           t.x = (const uint8_t*)in; t.w2 = it->second.first; t.bias = d.bias; t.y = out;
           t.B = batch; t.H = L.H; t.W = L.W; t.Ho = L.Ho; t.Wo = L.Wo; t.cout = L.cout;
           t.ka = g.ka; t.kb = g.kb; t.pt2 = g.pt2; t.pl2 = g.pl2; t.act = act;
+          t.use_window = stem_window;
           const size_t need = (size_t)batch * (L.Ho + g.ka - 1) * (L.Wo + g.kb - 1) * 32;
           if (need > stem_scratch.bytes) {
             cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // previous users of the old buffer
@@ -362,6 +393,14 @@ struct hfr_model {
           break;
         }
         case L_CONV: {
+          if (d.w_win != nullptr && L.in2 < 0) {
+            WinArgs w;
+            w.x = in; w.w = d.w_win; w.bias = d.bias; w.y = out; w.B = batch; w.H = L.H; w.W = L.W; w.cin = L.cin;
+            w.Ho = L.Ho; w.Wo = L.Wo; w.cout = L.cout; w.kh = L.kh; w.kw = L.kw; w.pad_t = L.pad_t; w.pad_l = L.pad_l;
+            w.act = act; w.plane_major = 0;
+            launch_conv_window(w, device, s);
+            break;
+          }
           ConvArgs a;
           a.x = in; a.w = d.w; a.bias = d.bias;
           a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
@@ -489,14 +528,8 @@ int hfr_model_load(const char* path, const char* input_name, const char* output_
     m->precision = precision;
     m->device = device;
     static const uint8_t kHdf5Magic[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
-    if (data.size() >= 8 && memcmp(data.data(), kHdf5Magic, 8) == 0) {
-      m->plan = compile_keras_mobilenet_h5(data.data(), data.size(), input_hw);
-    } else {
-      if (!input_name || !output_names_csv) throw Error(HFR_ERR_INVALID, "input/output tensor names are required");
-      Graph g;
-      parse_graphdef(data.data(), data.size(), &g);
-      CompileOptions opt;
-      opt.input_name = input_name;
+    CompileOptions opt;
+    if (output_names_csv) {
       std::stringstream ss(output_names_csv);
       std::string tok;
       while (std::getline(ss, tok, ',')) {
@@ -504,9 +537,19 @@ int hfr_model_load(const char* path, const char* input_name, const char* output_
         while (!tok.empty() && tok.back() == ' ') tok.pop_back();
         if (!tok.empty()) opt.output_names.push_back(tok);
       }
-      if (phase_name && *phase_name) opt.phase_name = phase_name;
-      opt.phase_value = phase_value;
-      opt.override_hw = input_hw;
+    }
+    if (phase_name && *phase_name) opt.phase_name = phase_name;
+    opt.phase_value = phase_value;
+    opt.override_hw = input_hw;
+    if (data.size() >= 8 && memcmp(data.data(), kHdf5Magic, 8) == 0) {
+      opt.phase_name.clear();  // a Keras weight file has no learning-phase conditionals
+      m->plan = compile_keras_mobilenet_h5(data.data(), data.size(), input_hw, opt);
+    } else {
+      if (!input_name || !*input_name || opt.output_names.empty())
+        throw Error(HFR_ERR_INVALID, "input/output tensor names are required");
+      Graph g;
+      parse_graphdef(data.data(), data.size(), &g);
+      opt.input_name = input_name;
       m->plan = compile_graph(g, opt);
     }
     m->plan_arena();
@@ -825,8 +868,11 @@ int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias
     std::vector<uint16_t> w2 = stem_tc_weights(wv, kh, kw, cout, pad_t, pad_l, flip, scale, mean, &g);
     DevBuf scratch;
     scratch.ensure((size_t)batch * (ho + g.ka - 1) * (wo + g.kb - 1) * 32);
+    const bool win = window_enabled();
+    if (win) w2 = stem_window_layout(w2, g.ka * g.kb, cout);
     void* w2d = upload(w2.data(), w2.size() * 2);
     StemTcArgs t;
+    t.use_window = win;
     t.x = (const uint8_t*)x_u8; t.scratch = scratch.p; t.w2 = w2d; t.bias = bias; t.y = y;
     t.B = batch; t.H = h; t.W = w_; t.Ho = ho; t.Wo = wo; t.cout = cout;
     t.ka = g.ka; t.kb = g.kb; t.pt2 = g.pt2; t.pl2 = g.pl2; t.act = act;
@@ -838,6 +884,27 @@ int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias
       throw;
     }
     cudaFree(w2d);
+  });
+}
+
+int hfr_op_conv2d_window(const void* x, const float* w_host, const float* bias, void* y, int batch, int h, int w_,
+                         int cin, int kh, int kw, int pad_t, int pad_l, int ho, int wo, int cout, int act, int device,
+                         void* stream) {
+  return guarded([&] {
+    use_device(device);
+    std::vector<uint16_t> hw = conv_window_layout(w_host, cout, kh * kw, cin);
+    void* wd = upload(hw.data(), hw.size() * 2);
+    WinArgs a;
+    a.x = x; a.w = wd; a.bias = bias; a.y = y; a.B = batch; a.H = h; a.W = w_; a.cin = cin; a.Ho = ho; a.Wo = wo;
+    a.cout = cout; a.kh = kh; a.kw = kw; a.pad_t = pad_t; a.pad_l = pad_l; a.act = act; a.plane_major = 0;
+    try {
+      launch_conv_window(a, device, (cudaStream_t)stream);
+      cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+    } catch (...) {
+      cudaFree(wd);
+      throw;
+    }
+    cudaFree(wd);
   });
 }
 

@@ -1,0 +1,244 @@
+// "Window" implicit-GEMM convolution for sm_100a: KHxKW stride-1 convolution over an NHWC bf16 tensor with Cout <= 64,
+// where every activation byte crosses L2->SM once per tile and the weights stay resident in shared memory.
+//
+//   * M tile = 16 (rows) x 8 (columns) output pixels of one image.  Cin/8 TMA loads (one per 8-channel plane) bring the
+//     (16+KH-1) x (8+KW-1) input window into smem as channel planes [Cin/8][wh][ww][8 ch = 16 B]; out-of-image pixels
+//     are zero-filled by the TMA unit = the convolution's zero padding.
+//   * The tensor core reads that window IN PLACE: with the no-swizzle K-major canonical layout a UMMA operand is
+//     "8-row groups of 16-byte rows", group stride SBO, k-chunk stride LBO.  8 horizontally adjacent pixels of a plane
+//     are exactly such a group (16-B pitch), the 16 tile rows are 16 groups at SBO = ww*16 B, and the second 8 channels
+//     of a K=16 step are the next plane at LBO = wh*ww*16 B.  Tap (r,s) is just a different start address.  No im2col
+//     copy exists anywhere - neither in HBM nor in smem.
+//   * Weights [taps][Cin/8][64 rows][16 B] are loaded once per (persistent) CTA.
+//   * Epilogue: two warpgroups ping-pong on tiles; bias + ReLU/ReLU6 -> bf16 -> swizzled staging -> 4-D TMA store
+//     (partial tiles are clipped by the TMA unit).
+//
+// Used for the stem (after space-to-depth, see stem_s2d_kernel: 7x7/2 -> 4x4/1 over 16 channels) and for 3x3 convolutions
+// with 64 output channels (ResNet stage 2), which the generic im2col-TMA path leaves L2-bandwidth-bound.
+#pragma once
+#include "ptx.cuh"
+
+namespace hfr {
+
+struct WinParams {
+  int tiles_x, tiles_y, num_tiles;  // per image: ceil(Wo/8) x ceil(Ho/16); num_tiles = B * tiles_x * tiles_y
+  int taps_h, taps_w;
+  int planes;                       // Cin / 8
+  int ww, wh;                       // window size in pixels
+  int pad_l, pad_t;
+  int N;                            // real output channels (<= 64)
+  const float* bias;
+  int act;
+  int w_chunks;                     // taps_h * taps_w * planes  (16-byte k-chunks of the weight matrix)
+  int plane_major;                  // input is [B][planes][H][W][8]: the whole window is ONE TMA box with long rows
+  int plane_pitch;                  // bytes between consecutive channel planes of a window in smem
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// K-major, no swizzle: 8-row groups of 16-byte rows; lbo = byte distance of the second 16-byte k-chunk, sbo = byte
+// distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+constexpr int kWinStages = 3;
+
+// dynamic smem: [1 KB align][weights w_bytes][kWinStages x window win_bytes (1 KB-rounded)][4 x 16 KB staging][barriers]
+__global__ void __launch_bounds__(384, 1)
+conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmD, const WinParams p, const int w_bytes, const int win_stride) {
+  constexpr int BLOCK_N = 64;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sW = smem_base;
+  const uint32_t sWin = sW + w_bytes;                      // w_bytes is a multiple of 1024
+  const uint32_t sEpi = sWin + kWinStages * win_stride;    // win_stride is a multiple of 1024
+  const uint32_t sBar = sEpi + 4 * 16384;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (sBar - smem_base) + 192);
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 32u + 8u * s; };
+  auto tfull_bar = [&](int s) { return sBar + 64u + 8u * s; };
+  auto tempty_bar = [&](int s) { return sBar + 80u + 8u * s; };
+  const uint32_t wfull_bar = sBar + 96u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < kWinStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t win_bytes = (uint32_t)p.planes * p.wh * p.ww * 16;               // bytes one window load delivers
+  const uint32_t plane_bytes = (uint32_t)p.plane_pitch;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights: resident for the lifetime of the CTA (3-D map {8, 64 rows, chunks}, one K=16 step = 2 chunks per box)
+      mbar_expect_tx(wfull_bar, (uint32_t)p.w_chunks * BLOCK_N * 16);
+      for (int c0 = 0; c0 < p.w_chunks; c0 += 2) tma_load_3d(sW + c0 * BLOCK_N * 16, &tmW, wfull_bar, 0, 0, c0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_img;
+        const int r = t - b * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), win_bytes);
+        if (p.plane_major) {
+          // [B][planes][H][W*8]: one box {ww*8, wh, planes, 1} - rows of ww*16 contiguous bytes
+          tma_load_4d(sWin + stage * win_stride, &tmX, full_bar(stage), (tx * 8 - p.pad_l) * 8, ty * 16 - p.pad_t, 0, b);
+        } else {
+          for (int pl = 0; pl < p.planes; ++pl)  // NHWC: one 8-channel plane per load: smem [plane][wh][ww][16 B]
+            tma_load_4d(sWin + stage * win_stride + pl * plane_bytes, &tmX, full_bar(stage), pl * 8, tx * 8 - p.pad_l,
+                        ty * 16 - p.pad_t, b);
+        }
+        if (++stage == kWinStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(1, 128, BLOCK_N);
+      const uint32_t sbo_a = (uint32_t)p.ww * 16;
+      const int ksteps = p.planes >> 1;  // K=16 (two 8-channel planes) per MMA
+      mbar_wait(wfull_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0, tile = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tile) {
+        const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const uint32_t win = sWin + stage * win_stride;
+        uint32_t first = 0;
+        for (int r = 0; r < p.taps_h; ++r) {
+          for (int s = 0; s < p.taps_w; ++s) {
+            const uint32_t a_tap = win + (uint32_t)(r * p.ww + s) * 16;
+            const uint32_t b_tap = sW + (uint32_t)((r * p.taps_w + s) * p.planes) * (BLOCK_N * 16);
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t adesc = umma_desc_noswz(a_tap + (uint32_t)(2 * j) * plane_bytes, plane_bytes, sbo_a);
+              const uint64_t bdesc = umma_desc_noswz(b_tap + (uint32_t)(2 * j) * (BLOCK_N * 16), BLOCK_N * 16, 128);
+              umma<false>(d_tmem, adesc, bdesc, idesc, first);
+              first = 1;
+            }
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == kWinStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    const uint32_t bar_id = 1 + g;
+    const bool leader = (ew == 0 && lane == 0);
+    const uint32_t as = g;
+    uint32_t tile = 0, my_tiles = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tile) {
+      if ((tile & 1) != (uint32_t)g) continue;
+      const int b = t / tiles_per_img;
+      const int rr = t - b * tiles_per_img;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const uint32_t aphase = my_tiles & 1;
+      const uint32_t buf = my_tiles & 1;
+      ++my_tiles;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      if (leader) tma_store_wait_read<1>();
+      named_bar_sync(bar_id, 128);
+      const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + h * 32, r);
+        tmem_ld_wait();
+        float v[32];
+        if (p.bias != nullptr && h * 32 < p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + h * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = __ldg(b4 + q);
+            v[4 * q] = __uint_as_float(r[4 * q]) + bb.x;
+            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z;
+            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j];
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          if (p.act == 2) x = fminf(fmaxf(x, 0.f), 6.f);
+          v[j] = x;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            w[e] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (leader) {
+        tma_store_4d(&tmD, sEpi + (g * 2 + buf) * 16384, 0, tx * 8, ty * 16, b);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace hfr

@@ -114,7 +114,9 @@ struct CompileOptions {
 // Switch/Merge, then fusion of conv -> scale -> shift -> (residual add) -> activation chains.
 Plan compile_graph(const Graph& g, const CompileOptions& opt);
 
-// Keras HDF5 weights (models/vgg2_mobilenet.h5, facerec_test.py:326-334) -> the same plan.
-Plan compile_keras_mobilenet_h5(const uint8_t* data, size_t size, int input_hw);
+// Keras HDF5 weights (models/vgg2_mobilenet.h5, facerec_test.py:326-334) -> the same plan.  opt.output_names may name
+// reshape_1/Reshape:0 (default), global_pooling/Mean:0 and, when the head layers exist, feats/Relu:0,
+// age_pred/Softmax:0, gender_pred/Sigmoid:0.
+Plan compile_keras_mobilenet_h5(const uint8_t* data, size_t size, int input_hw, const CompileOptions& opt);
 
 }  // namespace hfr

@@ -129,8 +129,11 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn* __restrict__ 
 //                                 -mean term, so mean subtraction stays exact and padding stays exactly zero)
 // pt/pl are even and H/W are even, so a 2x2 block is entirely inside or entirely outside the image.  uint8 values are
 // exact in bf16.  The stride-2 conv then is a stride-1 (KH'/2)x(KW'/2) conv over S: 16 channels = one MMA K-step.
+// plane_major: S is stored as [B][2 planes][Hs][Ws][8] (window kernel: whole halo window in one TMA box) instead of
+// [B][Hs][Ws][16].
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ s,
-                                                       int B, int H, int W, int Hs, int Ws, int pt, int pl) {
+                                                       int B, int H, int W, int Hs, int Ws, int pt, int pl,
+                                                       int plane_major) {
   const long long total = (long long)B * Hs * Ws;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -157,9 +160,16 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const uint8_t* __restrict
       __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
       w[e] = *reinterpret_cast<uint32_t*>(&t);
     }
-    uint4* dst = reinterpret_cast<uint4*>(s + (size_t)i * 16);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (plane_major) {
+      const size_t plane = (size_t)Hs * Ws;
+      uint4* dst = reinterpret_cast<uint4*>(s) + ((size_t)b * 2 * plane + (size_t)Y * Ws + X);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[plane] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(s + (size_t)i * 16);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
 }
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "conv_window.cuh"
 #include "kernels.cuh"
 
 namespace hfr {
@@ -273,8 +274,17 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
   {
     const long long total = (long long)a.B * Hs * Ws;
     stem_s2d_kernel<<<grid_for(total, 256), 256, 0, s>>>(a.x, (__nv_bfloat16*)a.scratch, a.B, a.H, a.W, Hs, Ws, a.pt2,
-                                                          a.pl2);
+                                                          a.pl2, a.use_window);
     HFR_LAUNCH_CHECK("stem_s2d");
+  }
+  if (a.use_window) {
+    WinArgs w;
+    w.x = a.scratch; w.w = a.w2; w.bias = a.bias; w.y = a.y;
+    w.B = a.B; w.H = Hs; w.W = Ws; w.cin = 16; w.Ho = a.Ho; w.Wo = a.Wo; w.cout = a.cout;
+    w.kh = a.ka; w.kw = a.kb; w.pad_t = 0; w.pad_l = 0; w.act = a.act;
+    w.plane_major = 1;
+    launch_conv_window(w, device, s);
+    return;
   }
   const int64_t M = (int64_t)a.B * a.Ho * a.Wo;
   const uint64_t dims[4] = {16, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)a.B};
@@ -310,6 +320,70 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
   p.n_blocks_per_unit = 1;
   p.num_units = p.num_m_blocks;
   launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, tD, p, device, s);
+}
+
+// ---------------------------------------------------------------------------------------------- window conv
+static void window_smem(int cin, int kh, int kw, int* w_bytes, int* win_bytes, int* win_stride, int* total) {
+  const int planes = cin / 8;
+  *w_bytes = kh * kw * planes * 64 * 16;
+  *win_bytes = planes * (((16 + kh - 1) * (8 + kw - 1) * 16 + 127) / 128 * 128);  // planes at a 128-B aligned pitch
+  *win_stride = (*win_bytes + 1023) / 1024 * 1024;
+  *total = 1024 + *w_bytes + kWinStages * *win_stride + 4 * 16384 + 256;
+}
+bool conv_window_fits(int cin, int kh, int kw) {
+  if (cin % 16) return false;
+  int wb, wn, ws, tot;
+  window_smem(cin, kh, kw, &wb, &wn, &ws, &tot);
+  return tot <= 227 * 1024;
+}
+void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
+  if (a.cout > 64 || a.cout % 32 || !conv_window_fits(a.cin, a.kh, a.kw)) throw Error(-5, "window conv: unsupported shape");
+  int w_bytes, win_bytes, win_stride, total;
+  window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total);
+  const int planes = a.cin / 8;
+  const int ww = 8 + a.kw - 1, wh = 16 + a.kh - 1;
+  CUtensorMap tX;
+  const int plane_px = wh * ww * 16;
+  if (a.plane_major) {
+    if (ww * 8 > 256) throw Error(-5, "window conv: window row too long for one TMA box");
+    const uint64_t xd[4] = {(uint64_t)a.W * 8, (uint64_t)a.H, (uint64_t)planes, (uint64_t)a.B};
+    const uint64_t xs[3] = {(uint64_t)a.W * 16, (uint64_t)a.H * a.W * 16, (uint64_t)planes * a.H * a.W * 16};
+    const uint32_t xbox[4] = {(uint32_t)ww * 8, (uint32_t)wh, (uint32_t)planes, 1};
+    tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  } else {
+    const uint64_t xd[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    const uint64_t xs[3] = {(uint64_t)a.cin * 2, (uint64_t)a.W * a.cin * 2, (uint64_t)a.H * a.W * a.cin * 2};
+    const uint32_t xbox[4] = {8, (uint32_t)ww, (uint32_t)wh, 1};
+    tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  const int chunks = a.kh * a.kw * planes;
+  const uint64_t wd[3] = {8, 64, (uint64_t)chunks};
+  const uint64_t wst[2] = {16, 1024};
+  const uint32_t wbox[3] = {8, 64, 2};
+  CUtensorMap tW = make_tiled(a.w, PREC_BF16, 3, wd, wst, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  const uint64_t yd[4] = {(uint64_t)a.cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.B};
+  const uint64_t ys[3] = {(uint64_t)a.cout * 2, (uint64_t)a.Wo * a.cout * 2, (uint64_t)a.Ho * a.Wo * a.cout * 2};
+  const uint32_t ybox[4] = {64, 8, 16, 1};
+  CUtensorMap tD = make_tiled(a.y, PREC_BF16, 4, yd, ys, ybox, CU_TENSOR_MAP_SWIZZLE_128B);
+  WinParams p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_x = (a.Wo + 7) / 8;
+  p.tiles_y = (a.Ho + 15) / 16;
+  p.num_tiles = a.B * p.tiles_x * p.tiles_y;
+  p.taps_h = a.kh; p.taps_w = a.kw; p.planes = planes; p.ww = ww; p.wh = wh;
+  p.pad_l = a.pad_l; p.pad_t = a.pad_t; p.N = a.cout; p.bias = a.bias; p.act = a.act; p.w_chunks = chunks;
+  p.plane_major = a.plane_major;
+  p.plane_pitch = a.plane_major ? plane_px : (plane_px + 127) / 128 * 128;
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(conv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+               "cudaFuncSetAttribute(window smem)");
+    configured[device].store(true);
+  }
+  const int grid = p.num_tiles < device_sm_count(device) ? p.num_tiles : device_sm_count(device);
+  if (grid < 1) return;
+  conv_window_kernel<<<grid, 384, total, s>>>(tX, tW, tD, p, w_bytes, win_stride);
+  HFR_LAUNCH_CHECK("conv_window");
 }
 
 // ---------------------------------------------------------------------------------------------- simple kernels

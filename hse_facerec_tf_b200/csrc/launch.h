@@ -44,8 +44,21 @@ struct StemTcArgs {
   void* y;              // [B,Ho,Wo,cout] bf16
   int B, H, W, Ho, Wo, cout, ka, kb, pt2, pl2;   // pt2/pl2: even padding used by the staging kernel
   int act;
+  int use_window;       // 1: w2 is in window layout [taps*2][64][8] (conv_window_kernel); 0: [taps][cout][16] (STEM16 im2col)
 };
 void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s);
+
+// Window implicit-GEMM convolution (conv_window.cuh): stride 1, bf16, cout <= 64, weights [taps*cin/8][64][8] bf16.
+struct WinArgs {
+  const void* x;      // [B,H,W,cin] bf16
+  const void* w;      // packed by pack_window_weights
+  const float* bias;
+  void* y;            // [B,Ho,Wo,cout] bf16
+  int B, H, W, cin, Ho, Wo, cout, kh, kw, pad_t, pad_l, act;
+  int plane_major;    // x is [B][cin/8][H][W][8] instead of NHWC
+};
+bool conv_window_fits(int cin, int kh, int kw);
+void launch_conv_window(const WinArgs& a, int device, cudaStream_t s);
 
 struct DwArgs {
   const void* x;      // [B,H,W,C] of T

@@ -304,3 +304,217 @@ def ensure_mobilenet_pb(seed=1234, input_hw=192) -> str:
     if not os.path.exists(p):
         write_mobilenet_pb(p, seed, input_hw)
     return p
+
+
+# ------------------------------------------------------------------------------------------- HDF5 (Keras weight files)
+class H5Writer:
+    """Minimal HDF5 writer producing what h5py/Keras 2.x write with default settings: superblock v0, version-1 object
+    headers, old-style groups (B-tree v1 + local heap + symbol table node), contiguous little-endian float32 datasets,
+    fixed-length string array attributes.  Groups hold at most 2*K entries per symbol table node (K = 256 here), which
+    is plenty for a Keras model."""
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    LEAF_K = 256
+
+    def __init__(self):
+        self.buf = bytearray(b"\0" * 96)      # superblock placeholder
+        self.root = {"groups": {}, "datasets": {}, "attrs": {}}
+
+    # -- tree construction -------------------------------------------------------------------------
+    def group(self, path):
+        node = self.root
+        for part in [p for p in path.split("/") if p]:
+            node = node["groups"].setdefault(part, {"groups": {}, "datasets": {}, "attrs": {}})
+        return node
+
+    def dataset(self, path, arr):
+        parts = [p for p in path.split("/") if p]
+        self.group("/".join(parts[:-1]))["datasets"][parts[-1]] = np.ascontiguousarray(arr, dtype="<f4")
+
+    def attr_strings(self, group_path, name, strings):
+        self.group(group_path)["attrs"][name] = [s.encode() if isinstance(s, str) else s for s in strings]
+
+    # -- low level -----------------------------------------------------------------------------------
+    def _alloc(self, data: bytes, align=8) -> int:
+        while len(self.buf) % align:
+            self.buf.append(0)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    @staticmethod
+    def _msg(mtype, body: bytes) -> bytes:
+        body = body + b"\0" * (-len(body) % 8)
+        return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+    def _object_header(self, msgs) -> int:
+        data = b"".join(msgs)
+        hdr = struct.pack("<BxHII4x", 1, len(msgs), 1, len(data))
+        return self._alloc(hdr + data)
+
+    @staticmethod
+    def _dataspace(dims) -> bytes:
+        return struct.pack("<BBB5x", 1, len(dims), 0) + b"".join(struct.pack("<Q", d) for d in dims)
+
+    @staticmethod
+    def _dtype_f32() -> bytes:
+        return struct.pack("<BBBBI", 0x11, 0x20, 31, 0, 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+
+    @staticmethod
+    def _dtype_str(n) -> bytes:
+        return struct.pack("<BBBBI", 0x13, 0x00, 0, 0, n)      # class 3 (string), null-terminated, ASCII
+
+    def _attr(self, name: str, strings) -> bytes:
+        n = max(len(s) for s in strings) + 1 if strings else 1
+        nm = name.encode() + b"\0"
+        dt, sp = self._dtype_str(n), self._dataspace([len(strings)])
+        pad = lambda b: b + b"\0" * (-len(b) % 8)   # noqa: E731
+        body = struct.pack("<BxHHH", 1, len(nm), len(dt), len(sp)) + pad(nm) + pad(dt) + pad(sp)
+        body += b"".join(s.ljust(n, b"\0") for s in strings)
+        return self._msg(0x000C, body)
+
+    def _write_dataset(self, arr) -> int:
+        addr = self._alloc(arr.tobytes()) if arr.size else self.UNDEF
+        layout = struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)
+        fill = struct.pack("<BBBB", 2, 2, 0, 0)   # fill value v2: alloc late, write never, undefined
+        return self._object_header([self._msg(0x0001, self._dataspace(arr.shape)), self._msg(0x0003, self._dtype_f32()),
+                                    self._msg(0x0005, fill), self._msg(0x0008, layout)])
+
+    def _write_group(self, node) -> int:
+        entries = {}
+        for name, sub in node["groups"].items():
+            entries[name] = self._write_group(sub)
+        for name, arr in node["datasets"].items():
+            entries[name] = self._write_dataset(arr)
+        names = sorted(entries)             # symbol table entries are ordered by name
+        if len(names) > 2 * self.LEAF_K:
+            raise ValueError("too many entries in one group for this writer")
+        heap_data = bytearray(b"\0" * 8)    # offset 0 = empty string
+        offs = {}
+        for nme in names:
+            offs[nme] = len(heap_data)
+            heap_data += nme.encode() + b"\0"
+            heap_data += b"\0" * (-len(heap_data) % 8)
+        seg = self._alloc(bytes(heap_data))
+        heap = self._alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), self.UNDEF, seg))
+        snod = b"SNOD" + struct.pack("<BxH", 1, len(names))
+        for nme in names:
+            snod += struct.pack("<QQII16x", offs[nme], entries[nme], 0, 0)
+        snod += b"\0" * (40 * (2 * self.LEAF_K - len(names)))
+        snod_addr = self._alloc(snod)
+        last_key = offs[names[-1]] if names else 0
+        tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if names else 0, self.UNDEF, self.UNDEF)
+        tree += struct.pack("<QQQ", 0, snod_addr, last_key)
+        tree += b"\0" * (16 * (2 * 16 - 1))      # room for 2K children, K = 16
+        tree_addr = self._alloc(tree)
+        msgs = [self._msg(0x0011, struct.pack("<QQ", tree_addr, heap))]
+        msgs += [self._attr(k, v) for k, v in node["attrs"].items()]
+        node["_btree"], node["_heap"] = tree_addr, heap
+        return self._object_header(msgs)
+
+    def save(self, path):
+        root_hdr = self._write_group(self.root)
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, 16, 0)
+        sb += struct.pack("<QQQQ", 0, self.UNDEF, len(self.buf), self.UNDEF)
+        sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", self.root["_btree"], self.root["_heap"])
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(self.buf)
+        return path
+
+
+def mobilenet_weights(seed=1234, width=1.0, heads=False):
+    """Seeded Keras-named MobileNet-v1 parameters: {'conv1/kernel': ..., 'conv1_bn/gamma': ..., ...}."""
+    rs = np.random.RandomState(seed)
+    w = {}
+
+    def ch(c):
+        return max(32, int(c * width) // 32 * 32)
+
+    def bn(name, c):
+        g, b, m, v = _bn_params(rs, c)
+        w[f"{name}/gamma"], w[f"{name}/beta"], w[f"{name}/moving_mean"], w[f"{name}/moving_variance"] = g, b, m, v
+
+    c0 = ch(32)
+    w["conv1/kernel"] = (rs.standard_normal((3, 3, 3, c0)) * np.sqrt(2.0 / 27) / 60.0).astype(np.float32)
+    bn("conv1_bn", c0)
+    cin = c0
+    for i, (cout, _) in enumerate(MOBILENET_CFG, start=1):
+        cout = ch(cout)
+        w[f"conv_dw_{i}/depthwise_kernel"] = (rs.standard_normal((3, 3, cin, 1)) * np.sqrt(2.0 / 9)).astype(np.float32)
+        bn(f"conv_dw_{i}_bn", cin)
+        w[f"conv_pw_{i}/kernel"] = (rs.standard_normal((1, 1, cin, cout)) * np.sqrt(2.0 / cin)).astype(np.float32)
+        bn(f"conv_pw_{i}_bn", cout)
+        cin = cout
+    if heads:
+        for name, (k, n) in (("feats", (cin, 256)), ("age_pred", (256, 100)), ("gender_pred", (256, 1))):
+            w[f"{name}/kernel"] = (rs.standard_normal((k, n)) * np.sqrt(1.0 / k)).astype(np.float32)
+            w[f"{name}/bias"] = rs.normal(0, 0.1, n).astype(np.float32)
+    return w
+
+
+def write_keras_mobilenet_h5(path, weights=None, seed=1234, full_model=True):
+    """models/vgg2_mobilenet.h5 stand-in.  full_model=True mimics model.save() (weights under /model_weights, as
+    facerec_keras_train.py:122 writes them); False mimics save_weights()."""
+    weights = weights or mobilenet_weights(seed)
+    h5 = H5Writer()
+    prefix = "model_weights/" if full_model else ""
+    layers = []
+    for key in weights:
+        layer = key.split("/")[0]
+        if layer not in layers:
+            layers.append(layer)
+    for key, arr in weights.items():
+        layer, wname = key.split("/")
+        h5.dataset(f"{prefix}{layer}/{layer}/{wname}:0", arr)
+    h5.attr_strings(prefix.rstrip("/"), "layer_names", layers)
+    h5.attr_strings(prefix.rstrip("/"), "backend", ["tensorflow"])
+    h5.attr_strings(prefix.rstrip("/"), "keras_version", ["2.2.4"])
+    for layer in layers:
+        names = [f"{k.split('/')[0]}/{k.split('/')[1]}:0" for k in weights if k.split("/")[0] == layer]
+        h5.attr_strings(f"{prefix}{layer}", "weight_names", names)
+    return h5.save(path)
+
+
+def write_mobilenet_pb_from_weights(path, weights, input_hw=192):
+    """The same parameters as a frozen GraphDef with FusedBatchNorm (eps 1e-3) - the oracle-side twin of the .h5."""
+    g = GraphWriter()
+    f = attr_type(DT_FLOAT)
+    g.node("input_1", "Placeholder", dtype=f, shape=attr_shape([-1, input_hw, input_hw, 3]))
+
+    def bn_relu6(layer, x):
+        for s in ("gamma", "beta", "moving_mean", "moving_variance"):
+            g.const(f"{layer}_bn/{s}", weights[f"{layer}_bn/{s}"])
+        y = g.node(f"{layer}_bn/FusedBatchNorm", "FusedBatchNorm",
+                   [x] + [f"{layer}_bn/{s}" for s in ("gamma", "beta", "moving_mean", "moving_variance")], T=f,
+                   epsilon=attr_f(1e-3), is_training=attr_b(False), data_format=attr_s(b"NHWC"))
+        return g.node(f"{layer}_relu/Relu6", "Relu6", [y], T=f)
+
+    x = bn_relu6("conv1", _conv(g, "conv1/convolution", "input_1", weights["conv1/kernel"], 2, b"SAME"))
+    for i, (_, stride) in enumerate(MOBILENET_CFG, start=1):
+        g.const(f"conv_dw_{i}/depthwise_kernel", weights[f"conv_dw_{i}/depthwise_kernel"])
+        y = g.node(f"conv_dw_{i}/depthwise", "DepthwiseConv2dNative", [x, f"conv_dw_{i}/depthwise_kernel"], T=f,
+                   strides=attr_ints([1, stride, stride, 1]), padding=attr_s(b"SAME"), data_format=attr_s(b"NHWC"),
+                   dilations=attr_ints([1, 1, 1, 1]))
+        x = bn_relu6(f"conv_dw_{i}", y)
+        x = bn_relu6(f"conv_pw_{i}", _conv(g, f"conv_pw_{i}/convolution", x, weights[f"conv_pw_{i}/kernel"], 1, b"SAME"))
+    g.const("global_pooling/Mean/reduction_indices", np.array([1, 2], np.int32))
+    x = g.node("global_pooling/Mean", "Mean", [x, "global_pooling/Mean/reduction_indices"], T=f, Tidx=attr_type(DT_INT32),
+               keep_dims=attr_b(False))
+    cin = weights["conv_pw_13/kernel"].shape[3]
+    g.const("reshape_1/Reshape/shape", np.array([-1, 1, 1, cin], np.int32))
+    g.node("reshape_1/Reshape", "Reshape", [x, "reshape_1/Reshape/shape"], T=f, Tshape=attr_type(DT_INT32))
+    if "feats/kernel" in weights:
+        def dense(name, xin, act):
+            g.const(f"{name}/kernel", weights[f"{name}/kernel"])
+            g.const(f"{name}/bias", weights[f"{name}/bias"])
+            m = g.node(f"{name}/MatMul", "MatMul", [xin, f"{name}/kernel"], T=f, transpose_a=attr_b(False),
+                       transpose_b=attr_b(False))
+            a = g.node(f"{name}/BiasAdd", "BiasAdd", [m, f"{name}/bias"], T=f)
+            return g.node(f"{name}/{act}", act, [a], T=f)
+        feats = dense("feats", x, "Relu")
+        dense("age_pred", feats, "Softmax")
+        dense("gender_pred", feats, "Sigmoid")
+    g.save(path)
+    return path

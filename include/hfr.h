@@ -132,6 +132,11 @@ int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* b
 int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias, void* y, int batch, int h, int w_,
                         int kh, int kw, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act, int device,
                         void* stream);
+/* Stride-1 KHxKW convolution, bf16, cout 32|64, through the smem-window kernel (conv_window.cuh).  w_host: HOST pointer
+ * [cout][kh*kw][cin] fp32; synchronises the stream before returning. */
+int hfr_op_conv2d_window(const void* x, const float* w_host, const float* bias, void* y, int batch, int h, int w_,
+                         int cin, int kh, int kw, int pad_t, int pad_l, int ho, int wo, int cout, int act, int device,
+                         void* stream);
 /* KxK convolution (square kernel, implicit GEMM on tensor cores; tf32/bf16 only). w: [cout][kh*kw][cin] of dtype. */
 int hfr_op_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int batch, int h,
                   int w_, int cin, int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int act,

@@ -111,3 +111,42 @@ def test_resnet50_caffe_style_plan(tmp_path):
     (ref,) = GraphOracle(pb).run(["pool5_7x7_s1:0"], {"input:0": x})
     got, _ = run_plan_cpu(m, x)
     np.testing.assert_allclose(got[0], ref.reshape(1, -1), rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("full_model", [True, False])
+def test_keras_h5_weights_file(tmp_path, full_model):
+    """models/vgg2_mobilenet.h5 (facerec_test.py:326-334): hand-written HDF5 reader (no libhdf5 / h5py in this image).
+    The fixture is written by hse_facerec_tf_b200.synth.H5Writer in the layout Keras 2.x + h5py produce by default
+    (superblock v0, v1 object headers, symbol-table groups, /model_weights/<layer>/<layer>/<weight>:0); the oracle
+    evaluates a .pb twin built from the same arrays."""
+    from hse_facerec_tf_b200.synth import mobilenet_weights, write_keras_mobilenet_h5, write_mobilenet_pb_from_weights
+    w = mobilenet_weights(seed=11, heads=full_model)
+    h5 = write_keras_mobilenet_h5(str(tmp_path / "vgg2_mobilenet.h5"), w, full_model=full_model)
+    pb = write_mobilenet_pb_from_weights(str(tmp_path / "twin.pb"), w, input_hw=96)
+    outs = ["reshape_1/Reshape:0"] + (["age_pred/Softmax:0", "gender_pred/Sigmoid:0"] if full_model else [])
+    m = hfr.HfrModel(h5, None, outs, device=None, input_hw=96)
+    assert (m.h, m.w) == (96, 96) and m.out_dims[0] == 1024
+    x = preprocess_rgb_u8(np.random.RandomState(4).randint(0, 256, (2, 96, 96, 3)).astype(np.uint8))
+    ref = GraphOracle(pb).run(outs, {"input_1:0": x})
+    got, _ = run_plan_cpu(m, x)
+    for g, r in zip(got, ref):
+        np.testing.assert_allclose(g, r.reshape(g.shape), rtol=1e-3, atol=1e-5)
+    # default size is the reference's sz=192 (facerec_test.py:325); default output is reshape_1
+    m192 = hfr.HfrModel(h5, None, [], device=None)
+    assert (m192.h, m192.w) == (192, 192) and m192.out_dims == [1024]
+
+
+def test_keras_h5_errors(tmp_path):
+    from hse_facerec_tf_b200.synth import H5Writer, mobilenet_weights, write_keras_mobilenet_h5
+    h5 = write_keras_mobilenet_h5(str(tmp_path / "ok.h5"), mobilenet_weights(seed=2))
+    data = open(h5, "rb").read()
+    (tmp_path / "trunc.h5").write_bytes(data[: len(data) // 3])
+    with pytest.raises(ValueError):
+        hfr.HfrModel(str(tmp_path / "trunc.h5"), None, [], device=None)
+    other = H5Writer()
+    other.dataset("model_weights/dense_1/dense_1/kernel:0", np.zeros((4, 4), np.float32))
+    other.save(str(tmp_path / "other.h5"))
+    with pytest.raises(ValueError, match="conv1"):
+        hfr.HfrModel(str(tmp_path / "other.h5"), None, [], device=None)
+    with pytest.raises(KeyError):
+        hfr.HfrModel(h5, None, ["age_pred/Softmax:0"], device=None)      # this file has no heads

@@ -216,6 +216,26 @@ def test_conv2d_implicit_gemm(prec, B, H, W, cin, cout, k, stride):
     assert (got - ref).abs().max().item() <= tol * (ref.abs().max().item() + 1.0)
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout,k", [(2, 56, 56, 64, 64, 3), (3, 28, 20, 64, 64, 3), (1, 9, 11, 32, 32, 3),
+                                             (2, 16, 16, 16, 64, 4), (1, 17, 23, 64, 64, 1)])
+def test_conv2d_window(B, H, W, cin, cout, k):
+    """smem-window implicit GEMM (no-swizzle UMMA descriptors over the TMA-loaded halo window) vs torch."""
+    g = torch.Generator(device="cpu").manual_seed(H * 5 + cin + k)
+    x = torch.randn(B, H, W, cin, generator=g).to(DEV).bfloat16().contiguous()
+    w = (torch.randn(cout, k, k, cin, generator=g) / (k * k * cin) ** 0.5).bfloat16().float().contiguous()
+    bias = torch.randn(cout, generator=g).to(DEV)
+    pad = (k - 1) // 2
+    ho, wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    y = torch.full((B, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    check(lib.hfr_op_conv2d_window(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, cin, k, k, pad, pad,
+                                   ho, wo, cout, 1, 0, _stream()))
+    xp = F.pad(x.double().permute(0, 3, 1, 2), (pad, pad, pad, pad))
+    ref = torch.relu(F.conv2d(xp, w.to(DEV).double().permute(0, 3, 1, 2), bias.double())).permute(0, 2, 3, 1)
+    got = y.double()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 2e-2 * (ref.abs().max().item() + 1.0)
+
+
 @pytest.mark.parametrize("prec", [1, 2])
 @pytest.mark.parametrize("explicit_zero", [0, 1])
 def test_maxpool(prec, explicit_zero):

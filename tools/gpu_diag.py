@@ -144,6 +144,33 @@ def diag_stem():
             print("   got[0,1,:4,1]", got[0, 1, :4, 1].tolist(), "ref", ref[0, 1, :4, 1].tolist())
 
 
+def diag_win():
+    for (B, H, W, cin, cout, k) in [(1, 16, 8, 16, 64, 1), (1, 16, 8, 16, 64, 3), (1, 16, 8, 64, 64, 3), (2, 56, 56, 64, 64, 3),
+                                    (1, 20, 13, 32, 32, 3), (3, 12, 12, 16, 64, 4)]:
+        g = torch.Generator().manual_seed(7)
+        x = torch.randint(-2, 3, (B, H, W, cin), generator=g).float().to(DEV).bfloat16()
+        w = torch.randint(-1, 2, (cout, k, k, cin), generator=g).float().contiguous()
+        pad = (k - 1) // 2
+        ho, wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+        y = torch.full((B, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        rc = lib.hfr_op_conv2d_window(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), B, H, W, cin, k, k, pad, pad, ho, wo, cout, 0, 0, None)
+        torch.cuda.synchronize()
+        if rc:
+            print(f"win {B}x{H}x{W}x{cin}->{cout} k{k}: rc={rc} {lib.hfr_last_error().decode()}")
+            continue
+        xp = F.pad(x.float().permute(0, 3, 1, 2), (pad, pad, pad, pad))
+        ref = F.conv2d(xp, w.to(DEV).permute(0, 3, 1, 2), None).permute(0, 2, 3, 1)
+        got = torch.nan_to_num(y.float(), nan=1e9)
+        bad = (got - ref).abs() > 0.01 * ref.abs() + 0.01
+        print(f"win {B}x{H}x{W}x{cin}->{cout} k{k}: mismatches={bad.sum().item()}/{bad.numel()}")
+        if bad.any():
+            print("   first bad (b,y,x,c):", bad.nonzero()[:6].tolist())
+            print("   bad per out row (img0):", bad[0].sum(dim=(1, 2)).tolist(), " per col:", bad[0].sum(dim=(0, 2)).tolist())
+            print("   bad per channel (img0):", bad[0].sum(dim=(0, 1)).tolist())
+            print("   got[0,0,:8,0]", got[0, 0, :8, 0].tolist(), "\n   ref[0,0,:8,0]", ref[0, 0, :8, 0].tolist())
+            print("   got[0,:8,0,0]", got[0, :8, 0, 0].tolist(), "\n   ref[0,:8,0,0]", ref[0, :8, 0, 0].tolist())
+
+
 def diag_knn():
     import hse_facerec_tf_b200 as hfr
     for prec in ("bf16", "tf32"):
@@ -190,6 +217,6 @@ if __name__ == "__main__":
     for w in what:
         print(f"===== {w}")
         try:
-            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv, "stem": diag_stem}[w]()
+            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv, "stem": diag_stem, "win": diag_win}[w]()
         except Exception:
             traceback.print_exc()

@@ -218,7 +218,22 @@ def bench_network(args, rank, world, dev):
     pk = peaks()
     work = plan_work(model.plan(), es)
     classes = {}
-    for w, t in zip(work, lms):
+    # a depthwise layer followed by a pointwise layer with an empty interval ran as ONE fused dwpw_kernel launch:
+    # book the pair as class "dwpw" (flops of both, bytes = depthwise input + pointwise output)
+    per_step = [t / max(lsteps, 1) for t in lms]
+    merged = []
+    i = 0
+    while i < len(work):
+        w, t = dict(work[i]), per_step[i]
+        if w["kind"] == "dw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 2e-4:
+            L0, L1 = model.plan()["layers"][i], model.plan()["layers"][i + 1]
+            w = dict(kind="dwpw", name=work[i + 1]["name"], flops=work[i]["flops"] + work[i + 1]["flops"],
+                     bytes=float((L0["hw_in"][0] * L0["hw_in"][1] * L0["cin"] + L1["hw_out"][0] * L1["hw_out"][1] * L1["cout"]) * es))
+            i += 1
+        merged.append((w, t))
+        i += 1
+    for w, t in merged:
+        t = t * max(lsteps, 1)
         c = classes.setdefault(w["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
         c["ms"] += t / max(lsteps, 1)
         c["flops"] += w["flops"] * batch
@@ -228,7 +243,7 @@ def bench_network(args, rank, world, dev):
     for kname, c in classes.items():
         if c["ms"] <= 0:
             continue
-        tensor_bound = kname in ("pw", "conv")
+        tensor_bound = kname in ("pw", "conv", "dwpw")
         ach = (c["flops"] / (c["ms"] * 1e-3) / 1e12) if tensor_bound else (c["bytes"] / (c["ms"] * 1e-3) / 1e9)
         peak = pk["tensor"] if tensor_bound else pk["hbm"]
         kernels[kname] = dict(ms_per_step=round(c["ms"], 5), launches=c["launches"],
@@ -237,7 +252,7 @@ def bench_network(args, rank, world, dev):
                               hbm_gbs=round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1))
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]
-    roof = dict(kernel={"pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col)", "dw": "dwconv3x3_kernel",
+    roof = dict(kernel={"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col)", "dw": "dwconv3x3_kernel",
                         "stem": "stem_conv_kernel"}.get(dom, dom),
                 bound=kd["bound"], achieved=kd["achieved"], peak=pk["tensor"] if kd["bound"] == "tensor" else pk["hbm"],
                 unit=kd["unit"], frac=kd["frac"], traffic=None, peak_source=pk["source"] + " (sustained)",

@@ -40,6 +40,7 @@ SIGNATURES = {
     "hfr_op_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "hfr_op_stem_conv": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_stem_conv_tc": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
+    "hfr_op_dwpw": (_i, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp]),
     "hfr_op_conv2d_window": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "hfr_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_maxpool": (_i, [_vp, _vp] + [_i] * 13 + [_vp]),

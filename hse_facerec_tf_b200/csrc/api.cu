@@ -176,6 +176,19 @@ struct hfr_model {
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
   int sub_batch = getenv("HFR_SUB_BATCH") ? atoi(getenv("HFR_SUB_BATCH")) : 0;
   bool stem_window = window_enabled();
+  bool fuse_dwpw = getenv("HFR_FUSE") != nullptr;  // experimental: measured slower than the two-kernel path
+  // layer i is a stride-1 depthwise whose only consumer is the 1x1 convolution at i+1: run both as dwpw_kernel
+  bool fused_pair(size_t i) const {
+    if (!fuse_dwpw || (keep_all && !getenv("HFR_FUSE_KEEP")) || precision != HFR_BF16 || i + 1 >= plan.layers.size()) return false;
+    const Layer& a = plan.layers[i];
+    const Layer& b = plan.layers[i + 1];
+    if (a.kind != L_DW || a.stride != 1 || a.pad_t != 1 || a.pad_l != 1 || b.kind != L_PW || b.in != a.out || b.in2 >= 0)
+      return false;
+    if (plan.values[(size_t)a.out].last_use != (int)i + 1) return false;
+    for (int o : plan.outputs)
+      if (o == a.out) return false;
+    return dwpw_supported(a.cin, b.cout) && a.act <= A_RELU6 && b.act <= A_RELU6;
+  }
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -247,10 +260,15 @@ struct hfr_model {
       val_bytes[(size_t)L.out] = value_image_bytes(L.out);
       val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
       if (keep_all) continue;
-      const int ins[2] = {L.in, L.in2};
+      // a fused depthwise+pointwise pair reads the depthwise INPUT while it writes the pointwise OUTPUT: the input must
+      // stay allocated until the pair's output has its own block
+      if (fused_pair((size_t)li)) continue;
+      int ins[3] = {L.in, L.in2, -1};
+      if (li > 0 && fused_pair((size_t)li - 1)) ins[2] = plan.layers[(size_t)li - 1].in;
       for (int v : ins) {
         if (v <= 0) continue;  // value 0 is the caller's input
-        if (plan.values[(size_t)v].last_use == li) release(val_off[(size_t)v], val_bytes[(size_t)v]);
+        const int lu = plan.values[(size_t)v].last_use;
+        if (lu == li || (v == ins[2] && lu == li - 1)) release(val_off[(size_t)v], val_bytes[(size_t)v]);
       }
       if (plan.values[(size_t)L.out].last_use < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
     }
@@ -331,6 +349,21 @@ struct hfr_model {
       const int act = L.act;  // A_NONE/A_RELU/A_RELU6 share values with the kernels' ACT_* codes
       const int round_out = rt && feeds_tensor_core(L.out);
       if (timing) cuda_check(cudaEventRecord(ev[2 * i], s), "cudaEventRecord");
+      if (fused_pair(i)) {
+        const Layer& P = plan.layers[i + 1];
+        DwPwArgs f;
+        f.x = in; f.dw_w = (const float*)d.w; f.dw_b = d.bias; f.pw_w = dev[i + 1].w; f.pw_b = dev[i + 1].bias;
+        f.y = vptr(P.out); f.B = batch; f.H = L.H; f.W = L.W; f.cin = L.cin; f.cout = P.cout; f.dw_act = L.act;
+        f.pw_act = P.act;
+        launch_dwpw(f, device, s);
+        if (timing) {   // the pair's time is booked on the depthwise layer; the pointwise layer records an empty interval
+          cuda_check(cudaEventRecord(ev[2 * i + 1], s), "cudaEventRecord");
+          cuda_check(cudaEventRecord(ev[2 * i + 2], s), "cudaEventRecord");
+          cuda_check(cudaEventRecord(ev[2 * i + 3], s), "cudaEventRecord");
+        }
+        ++i;
+        continue;
+      }
       switch (L.kind) {
         case L_STEM: {
           StemArgs a;
@@ -884,6 +917,17 @@ int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias
       throw;
     }
     cudaFree(w2d);
+  });
+}
+
+int hfr_op_dwpw(const void* x, const float* dw_w, const float* dw_b, const void* pw_w, const float* pw_b, void* y,
+                int batch, int h, int w_, int cin, int cout, int dw_act, int pw_act, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    DwPwArgs a;
+    a.x = x; a.dw_w = dw_w; a.dw_b = dw_b; a.pw_w = pw_w; a.pw_b = pw_b; a.y = y; a.B = batch; a.H = h; a.W = w_;
+    a.cin = cin; a.cout = cout; a.dw_act = dw_act; a.pw_act = pw_act;
+    launch_dwpw(a, device, (cudaStream_t)stream);
   });
 }
 

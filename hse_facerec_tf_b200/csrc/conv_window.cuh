@@ -94,6 +94,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const uint32_t win_bytes = (uint32_t)p.planes * p.wh * p.ww * 16;               // bytes one window load delivers

@@ -125,6 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel may run its prologue now ...
+  pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
 
   const int num_kb = (AMODE == AMODE_IM2COL)  ? p.conv_kw * p.conv_kw * p.conv_cblocks
                      : (AMODE == AMODE_STEM16) ? (p.conv_taps + 3) / 4

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn* __restrict__ 
     const int t = i >> 5, c = i & 31;
     s_w[i] = w[(size_t)t * p.Cout + cg * 32 + c];
   }
+  pdl_launch_dependents();
+  pdl_wait();
   __syncthreads();
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)p.B * p.Ho * p.Wo;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const uint8_t* __restrict
                                                        int B, int H, int W, int Hs, int Ws, int pt, int pl,
                                                        int plane_major) {
   const long long total = (long long)B * Hs * Ws;
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int X = (int)(i % Ws);
@@ -202,9 +206,11 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
   const int b = blockIdx.z;
   const uint32_t sm = smem_u32(dw_smem);
   const uint32_t sbar = smem_u32(&bar);
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(sbar, 1);
     fence_barrier_init();
+    pdl_wait();
     mbar_expect_tx(sbar, (uint32_t)(TWI * THI * cbe * sizeof(T)));
     tma_load_4d(sm, &tmX, sbar, c0, ox0 * STRIDE - p.pad_l, oy0 * STRIDE - p.pad_t, b);
   }
@@ -221,6 +227,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
   }
 #pragma unroll
   for (int e = 0; e < VN; ++e) bs[e] = __ldg(bias + c + e);
+  pdl_wait();       // outputs are written (and may alias the predecessor's inputs) only after it has completed
   __syncthreads();  // barrier init visible to all waiters
   mbar_wait(sbar, 0);
 
@@ -272,6 +279,8 @@ struct PoolParams {
 };
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, const PoolParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   const int cv = p.C / VN;
   const long long total = (long long)p.B * p.Ho * p.Wo * cv;
@@ -311,6 +320,8 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, const
 template <typename T>
 __global__ void subsample_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho,
                                  int Wo, int s) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   const int cv = C / VN;
   const long long total = (long long)B * Ho * Wo * cv;
@@ -331,6 +342,8 @@ __global__ void subsample_kernel(const T* __restrict__ x, T* __restrict__ y, int
 // per CTA, slices combined through shared memory.  Matches TF Mean(axis=[1,2]) / AvgPool(HxW, VALID).
 template <typename T>
 __global__ void __launch_bounds__(256) gap_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   __shared__ float red[8][32][VN];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -364,16 +377,23 @@ __global__ void __launch_bounds__(256) gap_kernel(const T* __restrict__ x, float
 
 // ------------------------------------------------------------------------------------------------------------------
 // Dense head: y[B,N] = act(x[B,K] * W[K,N] + bias), fp32.  act: 0 none, 1 relu, 3 sigmoid, 4 softmax (whole row in
-// one CTA).  CTA = 8 batch rows x up to 256 columns; x rows are staged in smem and broadcast.
+// one CTA, N <= COLS).  CTA = 8 batch rows x COLS columns; the K dimension is split over KS = 256/COLS thread slices
+// (independent, unrolled loads keep many weight rows in flight) and reduced through shared memory.
 enum { FC_NONE = 0, FC_RELU = 1, FC_SIGMOID = 3, FC_SOFTMAX = 4 };
+template <int COLS>
 __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                  const float* __restrict__ bias, float* __restrict__ y, int B, int K,
                                                  int N, int act) {
-  extern __shared__ float s_fc[];  // [8][K] inputs, [8][256] logits, [8][2] softmax stats
+  constexpr int KS = 256 / COLS;
+  extern __shared__ float s_fc[];  // [8][K] inputs | [KS][8][COLS] partials | [8][2] softmax stats
   float* sx = s_fc;
-  float* sl = s_fc + 8 * K;
+  float* sp = s_fc + 8 * K;
+  float* st = sp + KS * 8 * COLS;
   const int b0 = blockIdx.x * 8;
-  const int n = blockIdx.y * 256 + threadIdx.x;
+  const int col = threadIdx.x % COLS, ks = threadIdx.x / COLS;
+  const int n = blockIdx.y * COLS + col;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < 8 * K; i += 256) {
     const int r = i / K, k = i - r * K;
     sx[i] = (b0 + r < B) ? x[(size_t)(b0 + r) * K + k] : 0.f;
@@ -383,41 +403,61 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, co
 #pragma unroll
   for (int r = 0; r < 8; ++r) acc[r] = 0.f;
   if (n < N) {
-    for (int k = 0; k < K; ++k) {
+    const int kper = (K + KS - 1) / KS;
+    const int k0 = ks * kper, k1 = min(K, k0 + kper);
+    int k = k0;
+    for (; k + 16 <= k1; k += 16) {  // 16 independent weight loads in flight per thread
+      float ww[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) ww[u] = __ldg(w + (size_t)(k + u) * N + n);
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(sx[r * K + k + u], ww[u], acc[r]);
+    }
+    for (; k < k1; ++k) {
       const float ww = __ldg(w + (size_t)k * N + n);
 #pragma unroll
       for (int r = 0; r < 8; ++r) acc[r] = fmaf(sx[r * K + k], ww, acc[r]);
     }
-    const float bb = bias ? bias[n] : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sp[(ks * 8 + r) * COLS + col] = acc[r];
+  __syncthreads();
+  // threads of slice 0 own the final values
+  if (ks == 0) {
+    const float bb = (bias && n < N) ? bias[n] : 0.f;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      float v = acc[r] + bb;
+      float v = bb;
+#pragma unroll
+      for (int q = 0; q < KS; ++q) v += sp[(q * 8 + r) * COLS + col];
       if (act == FC_RELU) v = fmaxf(v, 0.f);
       if (act == FC_SIGMOID) v = 1.f / (1.f + expf(-v));
       acc[r] = v;
+      if (act == FC_SOFTMAX) sp[r * COLS + col] = (n < N) ? v : -INFINITY;  // slice 0's own slots: safe to overwrite
     }
   }
   if (act == FC_SOFTMAX) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sl[r * 256 + threadIdx.x] = (n < N) ? acc[r] : -INFINITY;
     __syncthreads();
     const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp r reduces row r
     float mx = -INFINITY;
-    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sl[wrp * 256 + j]);
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sp[wrp * COLS + j]);
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
-    for (int j = lane; j < N; j += 32) sum += expf(sl[wrp * 256 + j] - mx);
+    for (int j = lane; j < N; j += 32) sum += expf(sp[wrp * COLS + j] - mx);
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float* st = sl + 8 * 256;  // [8][2] (max, sum) per row
     if (lane == 0) {
       st[wrp * 2] = mx;
       st[wrp * 2 + 1] = sum;
     }
     __syncthreads();
+    if (ks == 0) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = expf(acc[r] - st[r * 2]) / st[r * 2 + 1];
+      for (int r = 0; r < 8; ++r) acc[r] = expf(acc[r] - st[r * 2]) / st[r * 2 + 1];
+    }
   }
-  if (n < N) {
+  if (ks == 0 && n < N) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       if (b0 + r < B) y[(size_t)(b0 + r) * N + n] = acc[r];

@@ -3,10 +3,13 @@
 #include "launch.h"
 
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <mutex>
 
 #include "conv_window.cuh"
+#include "dwpw.cuh"
 #include "kernels.cuh"
 
 namespace hfr {
@@ -22,6 +25,27 @@ void cuda_check(cudaError_t e, const char* what) {
     g_launches.fetch_add(1);                      \
     cuda_check(cudaGetLastError(), "launch " name); \
   } while (0)
+
+// Launch with the programmatic-dependent-launch attribute (every kernel launched through here calls pdl_wait()).
+static bool pdl_enabled() {
+  static const bool on = getenv("HFR_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cuda_check(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...), "cudaLaunchKernelEx");
+}
 
 int device_sm_count(int device) {
   static std::mutex mu;
@@ -107,7 +131,7 @@ static void launch_stem_t(const StemArgs& a, cudaStream_t s) {
   const long long npix = (long long)a.B * a.Ho * a.Wo;
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)(a.cout / 32));
   const size_t smem = (size_t)a.kh * a.kw * 3 * 32 * sizeof(float);
-  stem_conv_kernel<TIn, T><<<grid, 128, smem, s>>>((const TIn*)a.x, a.w, a.bias, (T*)a.y, p);
+  launch_pdl(stem_conv_kernel<TIn, T>, grid, dim3(128), smem, s, (const TIn*)a.x, a.w, a.bias, (T*)a.y, p);
   HFR_LAUNCH_CHECK("stem_conv");
 }
 void launch_stem(const StemArgs& a, int prec, cudaStream_t s) {
@@ -142,7 +166,7 @@ static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
   const int tiles_h = (a.Ho + 7) / 8;
   dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(a.C / cbe), (unsigned)a.B);
   const size_t smem = (size_t)TI * TI * cbe * es + 128;
-  dwconv3x3_kernel<T, STRIDE><<<grid, 16 * VL, smem, s>>>(tm, a.w, a.bias, (T*)a.y, p);
+  launch_pdl(dwconv3x3_kernel<T, STRIDE>, grid, dim3(16 * VL), smem, s, tm, a.w, a.bias, (T*)a.y, p);
   HFR_LAUNCH_CHECK("dwconv3x3");
 }
 void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
@@ -170,7 +194,7 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
   }
   int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
   if (grid < 1) return;
-  kern<<<grid, 384, SM::kTotal, s>>>(tA, tB, tD, tR, p);
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB, tD, tR, p);
   HFR_LAUNCH_CHECK("gemm_tc");
 }
 
@@ -273,8 +297,8 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
   const int Hs = a.Ho + a.ka - 1, Ws = a.Wo + a.kb - 1;
   {
     const long long total = (long long)a.B * Hs * Ws;
-    stem_s2d_kernel<<<grid_for(total, 256), 256, 0, s>>>(a.x, (__nv_bfloat16*)a.scratch, a.B, a.H, a.W, Hs, Ws, a.pt2,
-                                                          a.pl2, a.use_window);
+    launch_pdl(stem_s2d_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, a.x, (__nv_bfloat16*)a.scratch, a.B, a.H, a.W,
+               Hs, Ws, a.pt2, a.pl2, a.use_window);
     HFR_LAUNCH_CHECK("stem_s2d");
   }
   if (a.use_window) {
@@ -382,8 +406,59 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   }
   const int grid = p.num_tiles < device_sm_count(device) ? p.num_tiles : device_sm_count(device);
   if (grid < 1) return;
-  conv_window_kernel<<<grid, 384, total, s>>>(tX, tW, tD, p, w_bytes, win_stride);
+  launch_pdl(conv_window_kernel, dim3(grid), dim3(384), (size_t)total, s, tX, tW, tD, p, w_bytes, win_stride);
   HFR_LAUNCH_CHECK("conv_window");
+}
+
+// ---------------------------------------------------------------------------------------------- fused dw + pw
+bool dwpw_supported(int cin, int cout) {
+  if (cin % 64 || cout % 64) return false;
+  const int bn = cout >= 256 ? 256 : cout;
+  if (cout % bn) return false;
+  const int fixed = bn == 256 ? DwPwSmem<256>::kFixed : bn == 128 ? DwPwSmem<128>::kFixed : DwPwSmem<64>::kFixed;
+  return fixed + (cin / 8) * kDwVecStride * 4 <= 227 * 1024;
+}
+template <int BN>
+static void launch_dwpw_t(const CUtensorMap& tX, const CUtensorMap& tB, const CUtensorMap& tD, const DwPwParams& p,
+                          int device, cudaStream_t s) {
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(dwpw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+               "cudaFuncSetAttribute(dwpw smem)");
+    configured[device].store(true);
+  }
+  const int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
+  if (grid < 1) return;
+  launch_pdl(dwpw_kernel<BN>, dim3(grid), dim3(384), (size_t)DwPwSmem<BN>::total(p.Cin), s, tX, tB, tD, p);
+  HFR_LAUNCH_CHECK("dwpw");
+}
+void launch_dwpw(const DwPwArgs& a, int device, cudaStream_t s) {
+  if (!dwpw_supported(a.cin, a.cout)) throw Error(-5, "fused dw+pw: unsupported channel counts");
+  DwPwParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cin = a.cin; p.Cout = a.cout;
+  if (a.H <= 8 && a.W <= 8) { p.tile_n = 2; p.tile_h = 8; } else { p.tile_n = 1; p.tile_h = 16; }
+  p.tiles_x = (a.W + 7) / 8;
+  p.tiles_y = (a.H + p.tile_h - 1) / p.tile_h;
+  p.img_groups = (a.B + p.tile_n - 1) / p.tile_n;
+  p.ww = 10; p.wh = p.tile_h + 2;
+  p.num_kb = a.cin / 64;
+  const int bn = a.cout >= 256 ? 256 : a.cout;
+  p.n_blocks = a.cout / bn;
+  p.num_units = p.img_groups * p.tiles_x * p.tiles_y * p.n_blocks;
+  p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pw_b = a.pw_b; p.dw_act = a.dw_act; p.pw_act = a.pw_act;
+  const uint64_t xd[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t xs[3] = {(uint64_t)a.cin * 2, (uint64_t)a.W * a.cin * 2, (uint64_t)a.H * a.W * a.cin * 2};
+  const uint32_t xbox[4] = {64, (uint32_t)p.ww, (uint32_t)p.wh, (uint32_t)p.tile_n};
+  CUtensorMap tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUtensorMap tB = make_tmap_2d(a.pw_w, PREC_BF16, (uint64_t)a.cout, (uint64_t)a.cin, (uint32_t)bn);
+  const uint64_t yd[4] = {(uint64_t)a.cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t ys[3] = {(uint64_t)a.cout * 2, (uint64_t)a.W * a.cout * 2, (uint64_t)a.H * a.W * a.cout * 2};
+  const uint32_t ybox[4] = {64, 8, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
+  CUtensorMap tD = make_tiled(a.y, PREC_BF16, 4, yd, ys, ybox, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (bn == 256) launch_dwpw_t<256>(tX, tB, tD, p, device, s);
+  else if (bn == 128) launch_dwpw_t<128>(tX, tB, tD, p, device, s);
+  else launch_dwpw_t<64>(tX, tB, tD, p, device, s);
 }
 
 // ---------------------------------------------------------------------------------------------- simple kernels
@@ -396,9 +471,9 @@ void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s) {
   if (a.C % vn) throw Error(-1, "maxpool: channels must be a multiple of the 16-byte vector");
   const long long total = (long long)a.B * a.Ho * a.Wo * (a.C / vn);
   if (prec == PREC_BF16)
-    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, p);
+    launch_pdl(maxpool_kernel<__nv_bfloat16>, dim3(grid_for(total, 256)), dim3(256), 0, s, (const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, p);
   else
-    maxpool_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)a.x, (float*)a.y, p);
+    launch_pdl(maxpool_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, s, (const float*)a.x, (float*)a.y, p);
   HFR_LAUNCH_CHECK("maxpool");
 }
 
@@ -407,31 +482,43 @@ void launch_subsample(const void* x, void* y, int B, int H, int W, int C, int Ho
   const int vn = prec == PREC_BF16 ? 8 : 4;
   const long long total = (long long)B * Ho * Wo * (C / vn);
   if (prec == PREC_BF16)
-    subsample_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B,
-                                                                          H, W, C, Ho, Wo, stride);
+    launch_pdl(subsample_kernel<__nv_bfloat16>, dim3(grid_for(total, 256)), dim3(256), 0, s, (const __nv_bfloat16*)x,
+               (__nv_bfloat16*)y, B, H, W, C, Ho, Wo, stride);
   else
-    subsample_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)x, (float*)y, B, H, W, C, Ho, Wo, stride);
+    launch_pdl(subsample_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, s, (const float*)x, (float*)y, B, H, W, C,
+               Ho, Wo, stride);
   HFR_LAUNCH_CHECK("subsample");
 }
 
 void launch_gap(const void* x, float* y, int B, int HW, int C, int prec, cudaStream_t s) {
   const int vn = prec == PREC_BF16 ? 8 : 4;
   dim3 grid((unsigned)B, (unsigned)((C / vn + 31) / 32));
-  if (prec == PREC_BF16) gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, y, HW, C);
-  else gap_kernel<float><<<grid, 256, 0, s>>>((const float*)x, y, HW, C);
+  if (prec == PREC_BF16) launch_pdl(gap_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)x, y, HW, C);
+  else launch_pdl(gap_kernel<float>, grid, dim3(256), 0, s, (const float*)x, y, HW, C);
   HFR_LAUNCH_CHECK("gap");
 }
 
+template <int COLS>
+static void launch_fc_t(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
+                        cudaStream_t s) {
+  const size_t smem = ((size_t)8 * K + 8 * 256 + 16) * sizeof(float);
+  cuda_check(cudaFuncSetAttribute(fc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+             "cudaFuncSetAttribute(fc smem)");
+  dim3 grid((unsigned)((B + 7) / 8), (unsigned)((N + COLS - 1) / COLS));
+  launch_pdl(fc_kernel<COLS>, grid, dim3(256), smem, s, x, w, bias, y, B, K, N, act);
+  HFR_LAUNCH_CHECK("fc");
+}
 void launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
                cudaStream_t s) {
   if (act == FC_SOFTMAX && N > 256) throw Error(-5, "dense+softmax: at most 256 classes");
-  const size_t smem = ((size_t)8 * K + 8 * 256 + 16) * sizeof(float);
-  if (smem > 200 * 1024) throw Error(-5, "dense: input dimension too large");
-  cuda_check(cudaFuncSetAttribute(fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-             "cudaFuncSetAttribute(fc smem)");
-  dim3 grid((unsigned)((B + 7) / 8), (unsigned)((N + 255) / 256));
-  fc_kernel<<<grid, 256, smem, s>>>(x, w, bias, y, B, K, N, act);
-  HFR_LAUNCH_CHECK("fc");
+  if (((size_t)8 * K + 8 * 256 + 16) * sizeof(float) > 200 * 1024) throw Error(-5, "dense: input dimension too large");
+  if (act == FC_SOFTMAX) {   // the whole row must live in one CTA
+    if (N <= 64) launch_fc_t<64>(x, w, bias, y, B, K, N, act, s);
+    else if (N <= 128) launch_fc_t<128>(x, w, bias, y, B, K, N, act, s);
+    else launch_fc_t<256>(x, w, bias, y, B, K, N, act, s);
+  } else {
+    launch_fc_t<32>(x, w, bias, y, B, K, N, act, s);   // 8 k-slices per column: short dependent-load chains
+  }
 }
 
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {

@@ -60,6 +60,19 @@ struct WinArgs {
 bool conv_window_fits(int cin, int kh, int kw);
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s);
 
+// Fused depthwise 3x3 (stride 1, SAME) + pointwise 1x1 block (dwpw.cuh), bf16.
+struct DwPwArgs {
+  const void* x;        // [B,H,W,cin] bf16
+  const float* dw_w;    // [9][cin]
+  const float* dw_b;    // [cin]
+  const void* pw_w;     // [cout][cin] bf16
+  const float* pw_b;    // [cout] or null
+  void* y;              // [B,H,W,cout] bf16
+  int B, H, W, cin, cout, dw_act, pw_act;
+};
+bool dwpw_supported(int cin, int cout);
+void launch_dwpw(const DwPwArgs& a, int device, cudaStream_t s);
+
 struct DwArgs {
   const void* x;      // [B,H,W,C] of T
   const float* w;     // [9][C]

@@ -166,6 +166,12 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerializationAllowed may start while its
+// predecessor in the stream is still running; everything that reads or writes global memory must come after pdl_wait()
+// (= predecessor grid complete and flushed).  pdl_launch_dependents() lets the next kernel start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

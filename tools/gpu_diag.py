@@ -171,6 +171,62 @@ def diag_win():
             print("   got[0,:8,0,0]", got[0, :8, 0, 0].tolist(), "\n   ref[0,:8,0,0]", ref[0, :8, 0, 0].tolist())
 
 
+def diag_dwpw():
+    for (B, H, W, cin, cout) in [(1, 16, 8, 64, 64), (2, 16, 16, 64, 128), (2, 12, 12, 128, 256), (3, 6, 6, 256, 512),
+                                 (2, 24, 24, 128, 128), (5, 7, 7, 512, 1024)]:
+        g = torch.Generator().manual_seed(9)
+        x = torch.randint(-2, 3, (B, H, W, cin), generator=g).float().to(DEV).bfloat16()
+        dw = torch.randint(-1, 2, (9, cin), generator=g).float().to(DEV)
+        dwb = torch.randint(-1, 2, (cin,), generator=g).float().to(DEV)
+        pw = torch.randint(-1, 2, (cout, cin), generator=g).float().to(DEV).bfloat16()
+        y = torch.full((B, H, W, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        rc = lib.hfr_op_dwpw(x.data_ptr(), dw.data_ptr(), dwb.data_ptr(), pw.data_ptr(), None, y.data_ptr(), B, H, W, cin, cout, 0, 0, 0, None)
+        torch.cuda.synchronize()
+        if rc:
+            print(f"dwpw {B}x{H}x{W}x{cin}->{cout}: rc={rc} {lib.hfr_last_error().decode()}")
+            continue
+        xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+        mid = F.conv2d(xp, dw.view(3, 3, cin).permute(2, 0, 1).unsqueeze(1), dwb, groups=cin)
+        mid = mid.bfloat16().float()      # the depthwise output is rounded to bf16 when it becomes the A operand
+        ref = torch.einsum("bchw,oc->bhwo", mid, pw.float())
+        got = torch.nan_to_num(y.float(), nan=1e9)
+        bad = (got - ref).abs() > 0.01 * ref.abs() + 0.01
+        print(f"dwpw {B}x{H}x{W}x{cin}->{cout}: mismatches={bad.sum().item()}/{bad.numel()}")
+        if bad.any():
+            print("   first bad (b,y,x,c):", bad.nonzero()[:6].tolist())
+            print("   bad per image:", bad.sum(dim=(1, 2, 3)).tolist(), "per row(img0):", bad[0].sum(dim=(1, 2)).tolist(),
+                  " per col:", bad[0].sum(dim=(0, 2)).tolist())
+            print("   got[0,0,:4,0]", got[0, 0, :4, 0].tolist(), "ref", ref[0, 0, :4, 0].tolist())
+
+
+def diag_fuserace():
+    """Is the fused dw+pw path deterministic / batch-invariant?  Per-layer comparison of the same images run at B=64 and B=70."""
+    import hse_facerec_tf_b200 as hfr
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pb = os.path.join(root, "tests", "golden", "age_gender_quantized.pb")
+    os.environ["HFR_FUSE_KEEP"] = "1"
+    m = hfr.HfrModel(pb, "input_1:0", ["global_pooling/Mean:0"], precision="bf16", input_hw=192)
+    m.keep_activations(True)
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.randint(0, 256, (70, 192, 192, 3)).astype(np.uint8)).cuda()
+    layers = m.plan()["layers"]
+    def run(b):
+        m.forward(x[:b].contiguous())
+        torch.cuda.synchronize()
+        return [m.layer_output(li, b).clone() for li in range(len(layers))]
+    a70, b70, a64 = run(70), run(70), run(64)
+    for li, L in enumerate(layers):
+        d_rep = (a70[li] - b70[li]).abs().max().item()
+        d_b = (a70[li][:64] - a64[li]).abs()
+        nbad = (d_b > 0).sum().item()
+        msg = f"layer {li:2d} {L['kind']:5s} {L['name'][:26]:26s} repeat-diff {d_rep:.4g}  B70-vs-B64 diff {d_b.max().item():.4g} ({nbad} elems)"
+        if nbad and L['kind'] in ('pw', 'conv', 'stem'):
+            idx = (d_b > 0).nonzero()
+            imgs = sorted(set(idx[:, 0].tolist()))[:10]
+            msg += f" imgs {imgs} first {idx[:3].tolist()}"
+        print(msg)
+
+
 def diag_knn():
     import hse_facerec_tf_b200 as hfr
     for prec in ("bf16", "tf32"):
@@ -217,6 +273,6 @@ if __name__ == "__main__":
     for w in what:
         print(f"===== {w}")
         try:
-            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv, "stem": diag_stem, "win": diag_win}[w]()
+            {"gemm": diag_gemm, "dw": diag_dw, "knn": diag_knn, "model": diag_model, "conv": diag_conv, "stem": diag_stem, "win": diag_win, "dwpw": diag_dwpw, "fuserace": diag_fuserace}[w]()
         except Exception:
             traceback.print_exc()

@@ -243,13 +243,18 @@ def bench_network(args, rank, world, dev):
     for kname, c in classes.items():
         if c["ms"] <= 0:
             continue
-        tensor_bound = kname in ("pw", "conv", "dwpw")
-        ach = (c["flops"] / (c["ms"] * 1e-3) / 1e12) if tensor_bound else (c["bytes"] / (c["ms"] * 1e-3) / 1e9)
-        peak = pk["tensor"] if tensor_bound else pk["hbm"]
+        # each class is compared with BOTH roofs (algorithmic flops vs measured bf16 peak, algorithmic bytes vs measured
+        # HBM copy bandwidth); the binding roof is the one it sits closer to
+        tf = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        gb = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+        frac_t, frac_h = tf / pk["tensor"], gb / pk["hbm"]
+        tensor_bound = kname in ("pw", "conv", "dwpw") and frac_t >= frac_h
         kernels[kname] = dict(ms_per_step=round(c["ms"], 5), launches=c["launches"],
-                              bound="tensor" if tensor_bound else "hbm", achieved=round(ach, 2),
-                              unit="TFLOP/s" if tensor_bound else "GB/s", frac=round(ach / peak, 4),
-                              hbm_gbs=round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1))
+                              bound="tensor" if tensor_bound else "hbm",
+                              achieved=round(tf if tensor_bound else gb, 2),
+                              unit="TFLOP/s" if tensor_bound else "GB/s",
+                              frac=round(frac_t if tensor_bound else frac_h, 4),
+                              tflops=round(tf, 2), hbm_gbs=round(gb, 1))
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]
     roof = dict(kernel={"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col)", "dw": "dwconv3x3_kernel",
@@ -257,6 +262,14 @@ def bench_network(args, rank, world, dev):
                 bound=kd["bound"], achieved=kd["achieved"], peak=pk["tensor"] if kd["bound"] == "tensor" else pk["hbm"],
                 unit=kd["unit"], frac=kd["frac"], traffic=None, peak_source=pk["source"] + " (sustained)",
                 per_launch_ms=round(kd["ms_per_step"] / kd["launches"], 5))
+    # DRAM traffic per launch of the dominant class, from the committed ncu launch list of this workload (if present)
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath)).get("classes", {}).get(dom)
+        if tr and batch == WORKLOADS[args.workload][1] and args.precision == "bf16":
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = f"profiles/traffic_{args.workload}.json (ncu, share of step {tr['share']})"
+            roof["algorithmic_bytes_per_launch"] = round(classes[dom]["bytes"] / classes[dom]["launches"])
     total = batch * world * args.steps
     value = total / (ms * 1e-3)
     out_bytes = sum(model.out_dims) * 4 * batch
@@ -271,7 +284,9 @@ def bench_network(args, rank, world, dev):
                 e2e=dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
                          d2h_bytes_per_step=out_bytes),
                 gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step),
-                clocks=clocks, roofline=roof, kernels=kernels)
+                clocks=clocks, roofline=roof, kernels=kernels,
+                **({"layers": [dict(kind=w["kind"], name=w["name"], us=round(t * 1e3, 2), gflop=round(w["flops"] * batch / 1e9, 2),
+                                    mb=round(w["bytes"] * batch / 1e6, 1)) for w, t in merged]} if args.layers else {}))
 
 
 # ------------------------------------------------------------------------------------------------------ 1-NN
@@ -429,6 +444,7 @@ def main():
     ap.add_argument("--gallery", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
+    ap.add_argument("--layers", action="store_true", help="add per-layer event timings to the JSON line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -97,6 +97,9 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         if self._pad:
             q = torch.nn.functional.pad(q, (0, self._pad))
         nq = q.shape[0]
+        if nq == 0:
+            empty = np.zeros((0, 1), np.int64)
+            return (np.zeros((0, 1), np.float64), empty) if return_distance else empty
         d2 = torch.empty(nq, dtype=torch.float32, device=q.device)
         idx = torch.empty(nq, dtype=torch.int64, device=q.device)
         dev = q.device.index or 0

@@ -32,6 +32,9 @@ struct WinParams {
   int w_chunks;                     // taps_h * taps_w * planes  (16-byte k-chunks of the weight matrix)
   int plane_major;                  // input is [B][planes][H][W][8]: the whole window is ONE TMA box with long rows
   int plane_pitch;                  // bytes between consecutive channel planes of a window in smem
+  int shifted;                      // plane-major only: taps_w copies of the window, copy s shifted by s pixels, each
+                                    // exactly 8 pixels wide -> every 8-row operand group is one aligned 128-byte line
+  int copy_pitch;                   // bytes between consecutive shifted copies
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -98,7 +101,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   pdl_wait();
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const uint32_t win_bytes = (uint32_t)p.planes * p.wh * p.ww * 16;               // bytes one window load delivers
+  const uint32_t win_bytes = p.shifted ? (uint32_t)p.taps_w * p.planes * p.wh * 128   // bytes the window loads deliver
+                                       : (uint32_t)p.planes * p.wh * p.ww * 16;
   const uint32_t plane_bytes = (uint32_t)p.plane_pitch;
 
   if (warp == 0) {
@@ -114,7 +118,11 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), win_bytes);
-        if (p.plane_major) {
+        if (p.plane_major && p.shifted) {
+          for (int sh = 0; sh < p.taps_w; ++sh)   // box {8 px * 8 ch, wh, planes, 1} starting sh pixels to the right
+            tma_load_4d(sWin + stage * win_stride + sh * p.copy_pitch, &tmX, full_bar(stage),
+                        (tx * 8 - p.pad_l + sh) * 8, ty * 16 - p.pad_t, 0, b);
+        } else if (p.plane_major) {
           // [B][planes][H][W*8]: one box {ww*8, wh, planes, 1} - rows of ww*16 contiguous bytes
           tma_load_4d(sWin + stage * win_stride, &tmX, full_bar(stage), (tx * 8 - p.pad_l) * 8, ty * 16 - p.pad_t, 0, b);
         } else {
@@ -131,7 +139,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1, 128, BLOCK_N);
-      const uint32_t sbo_a = (uint32_t)p.ww * 16;
+      const uint32_t sbo_a = p.shifted ? 128u : (uint32_t)p.ww * 16;
       const int ksteps = p.planes >> 1;  // K=16 (two 8-channel planes) per MMA
       mbar_wait(wfull_bar, 0);
       int stage = 0;
@@ -146,7 +154,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint32_t first = 0;
         for (int r = 0; r < p.taps_h; ++r) {
           for (int s = 0; s < p.taps_w; ++s) {
-            const uint32_t a_tap = win + (uint32_t)(r * p.ww + s) * 16;
+            const uint32_t a_tap = p.shifted ? win + (uint32_t)s * p.copy_pitch + (uint32_t)r * 128
+                                             : win + (uint32_t)(r * p.ww + s) * 16;
             const uint32_t b_tap = sW + (uint32_t)((r * p.taps_w + s) * p.planes) * (BLOCK_N * 16);
             for (int j = 0; j < ksteps; ++j) {
               const uint64_t adesc = umma_desc_noswz(a_tap + (uint32_t)(2 * j) * plane_bytes, plane_bytes, sbo_a);
@@ -207,20 +216,10 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j];
-          if (p.act == 1) x = fmaxf(x, 0.f);
-          if (p.act == 2) x = fminf(fmaxf(x, 0.f), 6.f);
-          v[j] = x;
-        }
-#pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-            w[e] = *reinterpret_cast<uint32_t*>(&b2);
-          }
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2_act(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], p.act);
           const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
         }

@@ -353,14 +353,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = v[j];
-              if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-              if (p.act == ACT_RELU6) x = fminf(fmaxf(x, 0.f), 6.f);
-              v[j] = x;
-            }
             if constexpr (sizeof(T) == 4) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = v[j];
+                if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+                if (p.act == ACT_RELU6) x = fminf(fmaxf(x, 0.f), 6.f);
+                v[j] = x;
+              }
               if (p.round_tf32) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
@@ -376,10 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int q = 0; q < 4; ++q) {
                 uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-                  w[e] = *reinterpret_cast<uint32_t*>(&b2);
-                }
+                for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2_act(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], p.act);
                 const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                              "r"(w[3]));

@@ -188,7 +188,7 @@ struct DwParams {
 };
 
 template <typename T, int STRIDE>
-__global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX,
                                                         const float* __restrict__ w,   // [9][C]
                                                         const float* __restrict__ bias,  // [C]
                                                         T* __restrict__ y, const DwParams p) {
@@ -219,12 +219,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
   const int lx = strip & 7;            // output column within the tile
   const int ly0 = (strip >> 3) * 4;    // first output row of the strip
   const int c = c0 + v * VN;
-  float wt[9][VN], bs[VN];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-#pragma unroll
-    for (int e = 0; e < VN; ++e) wt[t][e] = __ldg(w + (size_t)t * p.C + c + e);
-  }
+  float bs[VN];
 #pragma unroll
   for (int e = 0; e < VN; ++e) bs[e] = __ldg(bias + c + e);
   pdl_wait();       // outputs are written (and may alias the predecessor's inputs) only after it has completed
@@ -238,12 +233,19 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
     for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
   const T* tile_s = reinterpret_cast<const T*>(dw_smem);
   constexpr int NROWS = 3 * STRIDE + 3;  // input rows touched by 4 vertically adjacent outputs
+  // one filter column at a time: only 3 taps x VN weights are live (keeps the kernel at <= 80 registers -> 6 CTAs/SM)
 #pragma unroll
-  for (int r = 0; r < NROWS; ++r) {
-    const int iy = ly0 * STRIDE + r;
+  for (int s = 0; s < 3; ++s) {
+    float wk[3][VN];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int ix = lx * STRIDE + s;
+    for (int kr = 0; kr < 3; ++kr) {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) wk[kr][e] = __ldg(w + (size_t)(kr * 3 + s) * p.C + c + e);
+    }
+    const int ix = lx * STRIDE + s;
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+      const int iy = ly0 * STRIDE + r;
       float xv[VN];
       Vec16<T>::load(tile_s + ((size_t)(iy * TWI + ix) * VL + v) * VN, xv);
 #pragma unroll
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
         const int kr = r - o * STRIDE;  // filter row this input row hits for output o
         if (kr >= 0 && kr < 3) {
 #pragma unroll
-          for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wt[kr * 3 + s][e], acc[o][e]);
+          for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
         }
       }
     }
@@ -262,10 +264,18 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __grid_constant__ 
     for (int o = 0; o < 4; ++o) {
       const int oy = oy0 + ly0 + o;
       if (oy < p.Ho) {
-        float ov[VN];
+        T* dst = y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c;
+        if constexpr (sizeof(T) == 2) {
+          uint32_t w4[4];
 #pragma unroll
-        for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
-        Vec16<T>::store(y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c, ov);
+          for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2_act(acc[o][2 * e], acc[o][2 * e + 1], p.act);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        } else {
+          float ov[VN];
+#pragma unroll
+          for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
+          Vec16<T>::store(dst, ov);
+        }
       }
     }
   }

@@ -347,10 +347,12 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- window conv
-static void window_smem(int cin, int kh, int kw, int* w_bytes, int* win_bytes, int* win_stride, int* total) {
+static void window_smem(int cin, int kh, int kw, int* w_bytes, int* win_bytes, int* win_stride, int* total,
+                        bool shifted = false) {
   const int planes = cin / 8;
   *w_bytes = kh * kw * planes * 64 * 16;
-  *win_bytes = planes * (((16 + kh - 1) * (8 + kw - 1) * 16 + 127) / 128 * 128);  // planes at a 128-B aligned pitch
+  *win_bytes = shifted ? kw * planes * (16 + kh - 1) * 128
+                       : planes * (((16 + kh - 1) * (8 + kw - 1) * 16 + 127) / 128 * 128);  // planes at a 128-B pitch
   *win_stride = (*win_bytes + 1023) / 1024 * 1024;
   *total = 1024 + *w_bytes + kWinStages * *win_stride + 4 * 16384 + 256;
 }
@@ -363,7 +365,9 @@ bool conv_window_fits(int cin, int kh, int kw) {
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   if (a.cout > 64 || a.cout % 32 || !conv_window_fits(a.cin, a.kh, a.kw)) throw Error(-5, "window conv: unsupported shape");
   int w_bytes, win_bytes, win_stride, total;
-  window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total);
+  const bool shifted = a.plane_major && getenv("HFR_NO_SHIFTED") == nullptr;
+  window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total, shifted);
+  if (total > 227 * 1024) throw Error(-5, "window conv: shared memory budget exceeded");
   const int planes = a.cin / 8;
   const int ww = 8 + a.kw - 1, wh = 16 + a.kh - 1;
   CUtensorMap tX;
@@ -372,7 +376,7 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
     if (ww * 8 > 256) throw Error(-5, "window conv: window row too long for one TMA box");
     const uint64_t xd[4] = {(uint64_t)a.W * 8, (uint64_t)a.H, (uint64_t)planes, (uint64_t)a.B};
     const uint64_t xs[3] = {(uint64_t)a.W * 16, (uint64_t)a.H * a.W * 16, (uint64_t)planes * a.H * a.W * 16};
-    const uint32_t xbox[4] = {(uint32_t)ww * 8, (uint32_t)wh, (uint32_t)planes, 1};
+    const uint32_t xbox[4] = {(uint32_t)(shifted ? 8 : ww) * 8, (uint32_t)wh, (uint32_t)planes, 1};
     tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
   } else {
     const uint64_t xd[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
@@ -397,7 +401,9 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   p.taps_h = a.kh; p.taps_w = a.kw; p.planes = planes; p.ww = ww; p.wh = wh;
   p.pad_l = a.pad_l; p.pad_t = a.pad_t; p.N = a.cout; p.bias = a.bias; p.act = a.act; p.w_chunks = chunks;
   p.plane_major = a.plane_major;
-  p.plane_pitch = a.plane_major ? plane_px : (plane_px + 127) / 128 * 128;
+  p.plane_pitch = shifted ? wh * 128 : a.plane_major ? plane_px : (plane_px + 127) / 128 * 128;
+  p.shifted = shifted;
+  p.copy_pitch = planes * wh * 128;
   static std::atomic<bool> configured[64];
   if (!configured[device].load()) {
     cuda_check(cudaFuncSetAttribute(conv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),

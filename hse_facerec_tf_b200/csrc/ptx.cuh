@@ -176,6 +176,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Two fp32 values -> packed bf16x2 (lo in the low half) with the activation fused into the conversion:
+// act 0 none, 1 ReLU (cvt.relu), 2 ReLU6 (cvt.relu + packed min with 6.0; rounding is monotonic and 6.0 is exact in
+// bf16, so min(round(max(x,0)), 6) == round(min(max(x,0), 6))).
+__device__ __forceinline__ uint32_t pack_bf16x2_act(float lo, float hi, int act) {
+  uint32_t d;
+  if (act == 0) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    if (act == 2) asm("min.bf16x2 %0, %0, %1;" : "+r"(d) : "r"(0x40C040C0u));
+  }
+  return d;
+}
+
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));

@@ -129,3 +129,40 @@ def test_merge_of_shards_equals_single_gallery():
     np.testing.assert_array_equal(bi.cpu().numpy(), i_ref[:, 0])
     for gt, h in keep:
         lib.hfr_knn_free(h)
+
+
+def test_empty_and_tiny_inputs():
+    g = np.random.RandomState(0).randn(3, 64).astype(np.float32)
+    clf = hfr.KNeighborsClassifier(precision="tf32").fit(g, np.array([7, 8, 9]))
+    assert clf.predict(np.zeros((0, 64), np.float32)).shape == (0,)
+    d, i = clf.kneighbors(g[1:2])
+    assert i[0, 0] == 1 and d[0, 0] < 1e-6
+    with pytest.raises(ValueError):
+        clf.predict(np.zeros((2, 32), np.float32))          # wrong feature count, as sklearn
+    with pytest.raises(ValueError):
+        hfr.KNeighborsClassifier().fit(np.zeros((0, 64), np.float32), np.zeros(0))
+    with pytest.raises(ValueError):
+        hfr.KNeighborsClassifier(n_neighbors=3).fit(g, np.array([7, 8, 9]))
+
+
+def test_extract_then_identify_end_to_end(age_gender_pb, golden_dir):
+    """BASELINE config 5 as a parity case: uint8 crops -> GPU embeddings (L2-normalised in the same call) -> GPU 1-NN,
+    against oracle embeddings + scikit-learn (the reference's own pipeline, facerec_test.py:394-442)."""
+    from oracle.tfnet import GraphOracle, preprocess_rgb_u8
+    from tests.helpers import smooth_images
+    crops = np.load(f"{golden_dir}/face_crops_u8.npz")["c192"]
+    imgs = np.concatenate([crops, smooth_images(12, 192, 21)])
+    (ref,) = GraphOracle(age_gender_pb).run(["global_pooling/Mean:0"], {"input_1:0": preprocess_rgb_u8(imgs)})
+    ref = preprocessing.normalize(ref)
+    rs = np.random.RandomState(8)
+    distract = preprocessing.normalize(np.abs(rs.randn(20000, 1024)).astype(np.float32))   # embeddings are non-negative
+    gallery = np.concatenate([ref, distract]).astype(np.float32)
+    y = np.arange(len(gallery)) % 5000
+    sk_pred = neighbors.KNeighborsClassifier(n_neighbors=1, p=2).fit(gallery, y).predict(ref)
+    for precision in ("tf32", "bf16"):
+        tfi = hfr.TensorFlowInference(age_gender_pb, "input_1:0", "global_pooling/Mean:0", precision=precision, input_hw=192)
+        emb = tfi.extract_batch(torch.from_numpy(imgs).cuda(), l2norm=True)
+        clf = hfr.KNeighborsClassifier(n_neighbors=1, p=2, precision=precision).fit(gallery, y)
+        pred = clf.predict(emb)                      # CUDA tensor in, labels out
+        np.testing.assert_array_equal(pred, sk_pred)
+        np.testing.assert_array_equal(pred, y[: len(imgs)])

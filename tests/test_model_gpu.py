@@ -169,3 +169,29 @@ def test_resnet50_synthetic_parity(precision, tmp_path):
         g = m.layer_output(li, 2).cpu().numpy().reshape(kept[li].shape)
         err, scale = np.abs(g - kept[li]).max(), max(np.abs(kept[li]).max(), 1.0)
         assert np.isfinite(g).all() and err <= tol * scale * (1 + li / 8), f"layer {li} {L['kind']} {L['name']}: {err} / {scale}"
+
+
+def test_forward_argument_errors(age_gender_pb):
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", ["global_pooling/Mean:0"], precision="bf16")
+    x = torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        m.forward(x)                                  # empty batch
+    with pytest.raises(ValueError):
+        m.forward(torch.zeros((2, 224, 224, 3), dtype=torch.float16, device="cuda"))
+    with pytest.raises(ValueError):
+        m.forward(torch.zeros((2, 224, 224, 3), dtype=torch.uint8, device="cuda").permute(0, 2, 1, 3))
+    m.close()
+
+
+def test_keras_h5_on_gpu_matches_pb_twin(tmp_path):
+    """The Keras .h5 loader and the .pb loader must produce the same network on the GPU (same weights, two formats)."""
+    from hse_facerec_tf_b200.synth import mobilenet_weights, write_keras_mobilenet_h5, write_mobilenet_pb_from_weights
+    w = mobilenet_weights(seed=3)
+    h5 = write_keras_mobilenet_h5(str(tmp_path / "vgg2_mobilenet.h5"), w)
+    pb = write_mobilenet_pb_from_weights(str(tmp_path / "twin.pb"), w, input_hw=192)
+    u8 = np.random.RandomState(5).randint(0, 256, (5, 192, 192, 3)).astype(np.uint8)
+    a = hfr.TensorFlowInference(h5, None, "reshape_1/Reshape:0", precision="tf32").extract_batch(torch.from_numpy(u8).cuda())
+    b = hfr.TensorFlowInference(pb, "input_1:0", "reshape_1/Reshape:0", precision="tf32").extract_batch(torch.from_numpy(u8).cuda())
+    assert torch.equal(a, b)
+    (ref,) = GraphOracle(pb).run(["reshape_1/Reshape:0"], {"input_1:0": preprocess_rgb_u8(u8)})
+    assert cosine(a.cpu().numpy(), ref.reshape(5, -1)).min() > 0.9999

@@ -1,0 +1,55 @@
+"""profiles/traffic_<workload>.json from an ncu launch list (gpu time + dram bytes per launch), one bench step.
+usage: python tools/traffic_from_launches.py <launches.csv> <workload> <launches per step>"""
+import collections
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def kernel_class(name):
+    if "gemm_tc_kernel" in name:
+        mode = name.split("<")[1].split(">")[0].replace(" ", "").split(",")
+        epi, amode = mode[2], mode[3]
+        if epi == "1":
+            return "knn"
+        return {"0": "pw", "1": "conv", "2": "stem"}[amode]
+    for key, cls in (("conv_window", "stem"), ("stem_s2d", "stem"), ("stem_conv", "stem"), ("dwconv3x3", "dw"), ("dwpw", "dwpw"),
+                     ("maxpool", "maxpool"), ("subsample", "subsample"), ("gap_kernel", "gap"), ("fc_kernel", "fc")):
+        if key in name:
+            return cls
+    return "other"
+
+
+def main():
+    path, workload, per_step = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    lines = [l for l in open(path) if not l.startswith("==")]
+    by = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = by.setdefault(r["ID"], {"name": r["Kernel Name"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
+    launches = list(by.values())[:per_step]
+    agg = {}
+    for d in launches:
+        c = agg.setdefault(kernel_class(d["name"]), dict(launches=0, us=0.0, dram_bytes=0.0, l2_bytes=0.0))
+        c["launches"] += 1
+        c["us"] += d.get("gpu__time_duration.sum", 0.0)
+        c["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        c["l2_bytes"] += d.get("lts__t_bytes.sum", 0.0)
+    tot = sum(c["us"] for c in agg.values()) or 1.0
+    out = {"workload": workload, "source": os.path.basename(path), "note": "ncu --clock-control none --cache-control none, "
+           "one eager bench step; per-launch averages", "classes": {}}
+    for k, c in agg.items():
+        out["classes"][k] = dict(launches=c["launches"], us_total=round(c["us"], 1), share=round(c["us"] / tot, 4),
+                                 dram_bytes_per_launch=round(c["dram_bytes"] / c["launches"]),
+                                 l2_bytes_per_launch=round(c["l2_bytes"] / c["launches"]))
+    dst = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -187,21 +187,21 @@ struct DwParams {
   int C, Ho, Wo, pad_t, pad_l, tiles_w, act, round_tf32;
 };
 
-template <typename T, int STRIDE>
+template <typename T, int STRIDE, int TILE_H>
 __global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX,
                                                         const float* __restrict__ w,   // [9][C]
                                                         const float* __restrict__ bias,  // [C]
                                                         T* __restrict__ y, const DwParams p) {
   constexpr int VN = Vec16<T>::N;
   constexpr int TWI = 7 * STRIDE + 3;
-  constexpr int THI = 7 * STRIDE + 3;
+  constexpr int THI = (TILE_H - 1) * STRIDE + 3;   // TILE_H x 8 output pixels per CTA: more bytes in flight per SM
   extern __shared__ uint8_t dw_smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   uint8_t* dw_smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);  // TMA destination: 128-B aligned
   const int VL = blockDim.x >> 4;  // 16-byte vector lanes per pixel (4 or 8)
   const int cbe = VL * VN;         // channels per CTA
   const int tile = blockIdx.x;
-  const int ox0 = (tile % p.tiles_w) * 8, oy0 = (tile / p.tiles_w) * 8;
+  const int ox0 = (tile % p.tiles_w) * 8, oy0 = (tile / p.tiles_w) * TILE_H;
   const int c0 = blockIdx.y * cbe;
   const int b = blockIdx.z;
   const uint32_t sm = smem_u32(dw_smem);
@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant
   const int v = threadIdx.x % VL;
   const int strip = threadIdx.x / VL;  // 0..15
   const int lx = strip & 7;            // output column within the tile
-  const int ly0 = (strip >> 3) * 4;    // first output row of the strip
   const int c = c0 + v * VN;
   float bs[VN];
 #pragma unroll
@@ -225,56 +224,59 @@ __global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant
   pdl_wait();       // outputs are written (and may alias the predecessor's inputs) only after it has completed
   __syncthreads();  // barrier init visible to all waiters
   mbar_wait(sbar, 0);
-
-  float acc[4][VN];
-#pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
   const T* tile_s = reinterpret_cast<const T*>(dw_smem);
   constexpr int NROWS = 3 * STRIDE + 3;  // input rows touched by 4 vertically adjacent outputs
-  // one filter column at a time: only 3 taps x VN weights are live (keeps the kernel at <= 80 registers -> 6 CTAs/SM)
+  const int ox = ox0 + lx;
+#pragma unroll 1
+  for (int half = 0; half < TILE_H / 8; ++half) {
+    const int ly0 = half * 8 + (strip >> 3) * 4;  // first output row of this thread's strip of 4
+    float acc[4][VN];
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    float wk[3][VN];
+    for (int o = 0; o < 4; ++o)
 #pragma unroll
-    for (int kr = 0; kr < 3; ++kr) {
+      for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
+    // one filter column at a time: only 3 taps x VN weights are live (keeps the kernel at <= 80 registers -> 6 CTAs/SM)
 #pragma unroll
-      for (int e = 0; e < VN; ++e) wk[kr][e] = __ldg(w + (size_t)(kr * 3 + s) * p.C + c + e);
-    }
-    const int ix = lx * STRIDE + s;
+    for (int s = 0; s < 3; ++s) {
+      float wk[3][VN];
 #pragma unroll
-    for (int r = 0; r < NROWS; ++r) {
-      const int iy = ly0 * STRIDE + r;
-      float xv[VN];
-      Vec16<T>::load(tile_s + ((size_t)(iy * TWI + ix) * VL + v) * VN, xv);
+      for (int kr = 0; kr < 3; ++kr) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int kr = r - o * STRIDE;  // filter row this input row hits for output o
-        if (kr >= 0 && kr < 3) {
+        for (int e = 0; e < VN; ++e) wk[kr][e] = __ldg(w + (size_t)(kr * 3 + s) * p.C + c + e);
+      }
+      const int ix = lx * STRIDE + s;
 #pragma unroll
-          for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
+      for (int r = 0; r < NROWS; ++r) {
+        const int iy = ly0 * STRIDE + r;
+        float xv[VN];
+        Vec16<T>::load(tile_s + ((size_t)(iy * TWI + ix) * VL + v) * VN, xv);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int kr = r - o * STRIDE;  // filter row this input row hits for output o
+          if (kr >= 0 && kr < 3) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
+          }
         }
       }
     }
-  }
-  const int ox = ox0 + lx;
-  if (ox < p.Wo) {
+    if (ox < p.Wo) {
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const int oy = oy0 + ly0 + o;
-      if (oy < p.Ho) {
-        T* dst = y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c;
-        if constexpr (sizeof(T) == 2) {
-          uint32_t w4[4];
+      for (int o = 0; o < 4; ++o) {
+        const int oy = oy0 + ly0 + o;
+        if (oy < p.Ho) {
+          T* dst = y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c;
+          if constexpr (sizeof(T) == 2) {
+            uint32_t w4[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2_act(acc[o][2 * e], acc[o][2 * e + 1], p.act);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        } else {
-          float ov[VN];
+            for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2_act(acc[o][2 * e], acc[o][2 * e + 1], p.act);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          } else {
+            float ov[VN];
 #pragma unroll
-          for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
-          Vec16<T>::store(dst, ov);
+            for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
+            Vec16<T>::store(dst, ov);
+          }
         }
       }
     }

@@ -145,7 +145,7 @@ void launch_stem(const StemArgs& a, int prec, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise
-template <typename T, int STRIDE>
+template <typename T, int STRIDE, int TILE_H>
 static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
   constexpr int VN = Vec16<T>::N;
   const int es = (int)sizeof(T);
@@ -154,27 +154,40 @@ static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
   if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
   const int cbe = VL * VN;
   if (a.C % cbe) throw Error(-1, "depthwise: channels must be a multiple of the channel block");
-  constexpr int TI = 7 * STRIDE + 3;
+  constexpr int TWI = 7 * STRIDE + 3;
+  constexpr int THI = (TILE_H - 1) * STRIDE + 3;
   const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
   const uint64_t strides[3] = {(uint64_t)a.C * es, (uint64_t)a.W * a.C * es, (uint64_t)a.H * a.W * a.C * es};
-  const uint32_t box[4] = {(uint32_t)cbe, (uint32_t)TI, (uint32_t)TI, 1};
+  const uint32_t box[4] = {(uint32_t)cbe, (uint32_t)TWI, (uint32_t)THI, 1};
   CUtensorMap tm = make_tiled(a.x, prec, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   DwParams p;
   p.C = a.C; p.Ho = a.Ho; p.Wo = a.Wo; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
   p.tiles_w = (a.Wo + 7) / 8;
   p.act = a.act; p.round_tf32 = a.round_tf32;
-  const int tiles_h = (a.Ho + 7) / 8;
+  const int tiles_h = (a.Ho + TILE_H - 1) / TILE_H;
   dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(a.C / cbe), (unsigned)a.B);
-  const size_t smem = (size_t)TI * TI * cbe * es + 128;
-  launch_pdl(dwconv3x3_kernel<T, STRIDE>, grid, dim3(16 * VL), smem, s, tm, a.w, a.bias, (T*)a.y, p);
+  const size_t smem = (size_t)TWI * THI * cbe * es + 128;
+  auto kern = dwconv3x3_kernel<T, STRIDE, TILE_H>;
+  if (smem > 48 * 1024) {
+    static std::atomic<bool> configured{false};
+    if (!configured.load()) {
+      cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "dw smem attribute");
+      configured.store(true);
+    }
+  }
+  launch_pdl(kern, grid, dim3(16 * VL), smem, s, tm, a.w, a.bias, (T*)a.y, p);
   HFR_LAUNCH_CHECK("dwconv3x3");
 }
 void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
   if (a.B > 65535) throw Error(-1, "depthwise: batch too large for one launch");
+  // 16x8-pixel tiles (TILE_H = 16) were measured 40 % slower than 8x8 on B200 (fewer, longer-running CTAs): kept only
+  // as a template option
+  const bool tall = getenv("HFR_DW_TALL") != nullptr && a.Ho > 8;
   if (a.stride == 1) {
-    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 1>(a, prec, s); else launch_dw_t<float, 1>(a, prec, s);
+    if (prec == PREC_BF16) { if (tall) launch_dw_t<__nv_bfloat16, 1, 16>(a, prec, s); else launch_dw_t<__nv_bfloat16, 1, 8>(a, prec, s); }
+    else                   { if (tall) launch_dw_t<float, 1, 16>(a, prec, s); else launch_dw_t<float, 1, 8>(a, prec, s); }
   } else if (a.stride == 2) {
-    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 2>(a, prec, s); else launch_dw_t<float, 2>(a, prec, s);
+    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 2, 8>(a, prec, s); else launch_dw_t<float, 2, 8>(a, prec, s);
   } else {
     throw Error(-5, "depthwise: stride must be 1 or 2");
   }

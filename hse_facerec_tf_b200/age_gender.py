@@ -48,6 +48,20 @@ class FacialImageProcessing:
             return age.cpu().numpy(), gender.cpu().numpy(), feat.cpu().numpy(), probs.cpu().numpy()
         return age, gender, feat, probs
 
+    def process_boxes(self, img_rgb, bounding_boxes, graph=False):
+        """The face loop of process_image (facial_analysis.py:233-293) as ONE batch on the GPU: expand every detected box
+        by 10 px, clamp, crop, resize (cv2-exact) and run the network.  Returns (bboxes, ages, genders, features) with the
+        reference's list layout; detection itself (MTCNN) is upstream and not part of this class."""
+        from .staging import crop_resize, expand_and_clamp_boxes
+        img_h, img_w, _ = img_rgb.shape
+        bboxes = expand_and_clamp_boxes(bounding_boxes, img_h, img_w)
+        if not bboxes:
+            return [], [], [], []
+        crops = crop_resize(img_rgb, bboxes, (self.model.h, self.model.w))
+        age, gender, feat, _ = self.age_gender_batch(crops, graph=graph)
+        age, gender, feat = age.cpu().numpy(), gender.cpu().numpy(), feat.cpu().numpy()
+        return bboxes, [float(a) for a in age], [g for g in gender], [f for f in feat]
+
     # -- reference-compatible closure -------------------------------------------------------------------
     def load_age_gender(self, sess=None, graph=None):
         w, h = self.model.w, self.model.h

@@ -725,6 +725,16 @@ int hfr_age_gender_post(const float* age_probs, int batch, int n, float* age_out
   });
 }
 
+int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n,
+                       uint8_t* out, int out_h, int out_w, int device, void* stream) {
+  return guarded([&] {
+    if (!frames || !boxes || !out || n < 0 || n_frames <= 0 || frame_h <= 0 || frame_w <= 0 || out_h <= 0 || out_w <= 0)
+      throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_crop_resize(frames, frame_h, frame_w, (const int*)boxes, n, out, out_h, out_w, (cudaStream_t)stream);
+  });
+}
+
 int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, void* stream) {
   return guarded([&] {
     if (!x || !y || n < 0 || dim <= 0) throw Error(HFR_ERR_INVALID, "bad argument");

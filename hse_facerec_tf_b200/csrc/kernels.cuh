@@ -125,6 +125,58 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const TIn* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Input staging ("next" row 1 of the scope table): crop boxes out of an RGB uint8 frame and resize every crop to the
+// network input size, bit-exactly like cv2.resize(..., INTER_LINEAR) on uint8 - what age_gender_fun does per face
+// (facial_analysis.py:95) after process_image cropped the box (facial_analysis.py:236-267).
+// OpenCV's 8-bit path: 11-bit fixed-point weights  a = rint(w * 2048)  from  f = (float)((d + 0.5) * scale - 0.5),
+// horizontal pass in int32, vertical pass  ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// Along x the weight is forced to (2048, 0) outside [0, w-1); along y only the row index is clamped.
+struct ResizeCoef {
+  int i0, i1, w0, w1;
+};
+__device__ __forceinline__ ResizeCoef resize_coef(int d, int src, int dst, bool is_x) {
+  const double scale = (double)src / (double)dst;
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);   // no FMA contraction: must match the host
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (is_x) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  ResizeCoef c;
+  c.w0 = __float2int_rn(__fmul_rn(1.f - f, 2048.f));
+  c.w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  c.i0 = min(max(s, 0), src - 1);
+  c.i1 = min(max(s + 1, 0), src - 1);
+  return c;
+}
+// frames [F,H,W,3] u8; boxes [n][5] int32 = (frame, x1, y1, x2, y2) with 0 <= x1 < x2 <= W; out [n,oh,ow,3] u8
+__global__ void crop_resize_u8_kernel(const uint8_t* __restrict__ frames, int H, int W, const int* __restrict__ boxes,
+                                      int n, uint8_t* __restrict__ out, int oh, int ow) {
+  const long long total = (long long)n * oh * ow;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % ow);
+    const int dy = (int)((i / ow) % oh);
+    const int b = (int)(i / ((long long)ow * oh));
+    const int* bx = boxes + (size_t)b * 5;
+    const int x1 = bx[1], y1 = bx[2], cw = bx[3] - bx[1], ch = bx[4] - bx[2];
+    const uint8_t* src = frames + ((size_t)bx[0] * H + y1) * W * 3 + (size_t)x1 * 3;
+    const ResizeCoef cx = resize_coef(dx, cw, ow, true), cy = resize_coef(dy, ch, oh, false);
+    const uint8_t* r0 = src + (size_t)cy.i0 * W * 3;
+    const uint8_t* r1 = src + (size_t)cy.i1 * W * 3;
+    uint8_t* o = out + (size_t)i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = (int)r0[cx.i0 * 3 + c] * cx.w0 + (int)r0[cx.i1 * 3 + c] * cx.w1;
+      const int h1 = (int)r1[cx.i0 * 3 + c] * cx.w0 + (int)r1[cx.i1 * 3 + c] * cx.w1;
+      const int v = (((cy.w0 * (h0 >> 4)) >> 16) + ((cy.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Stem on the tensor cores, step 1: space-to-depth staging of the uint8 image for a stride-2 KHxKW convolution.
 //   S[b, Y, X, (dy*2+dx)*3 + j] = u8[b, 2Y+dy-pt, 2X+dx-pl, j]   (0 outside the image)      j = raw channel 0..2
 //   S[b, Y, X, 12..15]          = 1 inside the image, 0 in the padding ("valid" channels: they carry the folded

@@ -540,6 +540,14 @@ void launch_fc(const float* x, const float* w, const float* bias, float* y, int 
   }
 }
 
+void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
+                        cudaStream_t s) {
+  if (n <= 0) return;
+  const long long total = (long long)n * oh * ow;
+  crop_resize_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(frames, H, W, boxes, n, out, oh, ow);
+  HFR_LAUNCH_CHECK("crop_resize_u8");
+}
+
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {
   age_post_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(probs, age, B, N);
   HFR_LAUNCH_CHECK("age_post");

@@ -116,6 +116,9 @@ void launch_subsample(const void* x, void* y, int B, int H, int W, int C, int Ho
 void launch_gap(const void* x, float* y, int B, int HW, int C, int prec, cudaStream_t s);
 // act: 0 none, 1 relu, 3 sigmoid, 4 softmax
 void launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, cudaStream_t s);
+// crop + cv2-exact bilinear resize of uint8 RGB boxes: boxes [n][5] = (frame, x1, y1, x2, y2), device int32
+void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
+                        cudaStream_t s);
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s);
 void launch_l2norm(const float* x, float* y, int64_t n, int d, cudaStream_t s);
 void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream_t s);

@@ -94,6 +94,12 @@ int hfr_model_set_layer_timing(hfr_model* m, int enable);
 int hfr_model_get_layer_times(const hfr_model* m, double* ms_per_layer, int* steps);
 void hfr_model_free(hfr_model* m);
 
+/* Input staging: crop `n` boxes out of RGB uint8 frames [n_frames, frame_h, frame_w, 3] and resize each crop to
+ * out_h x out_w, bit-exactly like cv2.resize(face_img, (w, h)) (INTER_LINEAR, uint8) in age_gender_fun
+ * (facial_analysis.py:95) applied to face_img = img[y1:y2, x1:x2] (facial_analysis.py:267).  boxes: device int32
+ * [n][5] = (frame index, x1, y1, x2, y2), already clamped to the frame with x2 > x1, y2 > y1.  out: [n,out_h,out_w,3]. */
+int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n,
+                       uint8_t* out, int out_h, int out_w, int device, void* stream);
 /* age = 1 + sum_{i in top2} i * p_i / sum_{top2} p   (facial_analysis.py:113-124); age_probs [batch, n] float32. */
 int hfr_age_gender_post(const float* age_probs, int batch, int n, float* age_out, int device, void* stream);
 /* sklearn.preprocessing.normalize(X, norm='l2') (facerec_test.py:262,265,405); in-place allowed (y == x). */

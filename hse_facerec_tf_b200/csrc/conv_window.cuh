@@ -75,7 +75,7 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   auto tempty_bar = [&](int s) { return sBar + 80u + 8u * s; };
   const uint32_t wfull_bar = sBar + 96u;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -105,18 +105,23 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                                        : (uint32_t)p.planes * p.wh * p.ww * 16;
   const uint32_t plane_bytes = (uint32_t)p.plane_pitch;
 
+  // Producer and MMA issuer: the whole warp runs the loops (uniform control flow), one elected lane issues - see
+  // elect_one() in ptx.cuh.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // weights: resident for the lifetime of the CTA (3-D map {8, 64 rows, chunks}, one K=16 step = 2 chunks per box)
       mbar_expect_tx(wfull_bar, (uint32_t)p.w_chunks * BLOCK_N * 16);
       for (int c0 = 0; c0 < p.w_chunks; c0 += 2) tma_load_3d(sW + c0 * BLOCK_N * 16, &tmW, wfull_bar, 0, 0, c0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_img;
-        const int r = t - b * tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        mbar_wait(empty_bar(stage), phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_img;
+      const int r = t - b * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full_bar(stage), win_bytes);
         if (p.plane_major && p.shifted) {
           for (int sh = 0; sh < p.taps_w; ++sh)   // box {8 px * 8 ch, wh, planes, 1} starting sh pixels to the right
@@ -130,47 +135,54 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             tma_load_4d(sWin + stage * win_stride + pl * plane_bytes, &tmX, full_bar(stage), pl * 8, tx * 8 - p.pad_l,
                         ty * 16 - p.pad_t, b);
         }
-        if (++stage == kWinStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == kWinStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1, 128, BLOCK_N);
-      const uint32_t sbo_a = p.shifted ? 128u : (uint32_t)p.ww * 16;
-      const int ksteps = p.planes >> 1;  // K=16 (two 8-channel planes) per MMA
-      mbar_wait(wfull_bar, 0);
-      int stage = 0;
-      uint32_t phase = 0, tile = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tile) {
-        const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        const uint32_t win = sWin + stage * win_stride;
+    constexpr uint32_t idesc = umma_idesc(1, 128, BLOCK_N);
+    const uint32_t sbo_a = p.shifted ? 128u : (uint32_t)p.ww * 16;
+    const int ksteps = p.planes >> 1;  // K=16 (two 8-channel planes) per MMA
+    // Descriptors advance by adds on the address field (16-byte units): an N=64 MMA occupies the tensor core for only
+    // ~48 cycles (tools/microbench/mma_bench.cu), so the issue loop must be a handful of uniform-datapath instructions.
+    const uint64_t a_desc0 = umma_desc_noswz(sWin, plane_bytes, sbo_a);
+    const uint64_t b_desc0 = umma_desc_noswz(sW, BLOCK_N * 16, 128);
+    const uint32_t a_row_step = p.shifted ? 8u : (uint32_t)p.ww;                 // one window row
+    const uint32_t a_col_step = p.shifted ? (uint32_t)p.copy_pitch >> 4 : 1u;    // one window column
+    const uint32_t a_k_step = (2u * plane_bytes) >> 4, b_k_step = (2u * BLOCK_N * 16) >> 4;  // two 8-channel planes
+    mbar_wait(wfull_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0, tile = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tile) {
+      const uint32_t as = tile & 1, aphase = (tile >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      if (elect_one()) {
+        uint64_t a_row = a_desc0 + (uint64_t)((uint32_t)(stage * win_stride) >> 4);
+        uint64_t bd = b_desc0;
         uint32_t first = 0;
-        for (int r = 0; r < p.taps_h; ++r) {
-          for (int s = 0; s < p.taps_w; ++s) {
-            const uint32_t a_tap = p.shifted ? win + (uint32_t)s * p.copy_pitch + (uint32_t)r * 128
-                                             : win + (uint32_t)(r * p.ww + s) * 16;
-            const uint32_t b_tap = sW + (uint32_t)((r * p.taps_w + s) * p.planes) * (BLOCK_N * 16);
-            for (int j = 0; j < ksteps; ++j) {
-              const uint64_t adesc = umma_desc_noswz(a_tap + (uint32_t)(2 * j) * plane_bytes, plane_bytes, sbo_a);
-              const uint64_t bdesc = umma_desc_noswz(b_tap + (uint32_t)(2 * j) * (BLOCK_N * 16), BLOCK_N * 16, 128);
-              umma<false>(d_tmem, adesc, bdesc, idesc, first);
+        for (int r = 0; r < p.taps_h; ++r, a_row += a_row_step) {
+          uint64_t a_tap = a_row;
+          for (int s = 0; s < p.taps_w; ++s, a_tap += a_col_step) {
+            uint64_t ad = a_tap;
+            for (int j = 0; j < ksteps; ++j, ad += a_k_step, bd += b_k_step) {
+              umma<false>(d_tmem, ad, bd, idesc, first);
               first = 1;
             }
           }
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(as));
-        if (++stage == kWinStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == kWinStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp >= 4) {

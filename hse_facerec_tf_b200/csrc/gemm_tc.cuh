@@ -101,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int s) { return sBar + 144u + 8u * s; };
   auto rfull_bar = [&](int s) { return sBar + 160u + 8u * s; };  // residual tile landed in staging buffer s (0..3)
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -149,8 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -165,32 +165,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           im_n = t / p.conv_ho;
         }
         for (int nb = nb0; nb < nb0 + nbn; ++nb) {
+          int cb = 0, tap_r = 0, tap_s = 0;  // im2col: channel block and filter tap of this k-block
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), SM::kStageBytes);
-            if (AMODE == AMODE_IM2COL) {
-              int tap = kb / p.conv_cblocks;
-              int cb = kb - tap * p.conv_cblocks;
-              int r = tap / p.conv_kw, s = tap - r * p.conv_kw;
-              tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
-                                 im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
-                                 (uint16_t)(s * p.conv_dil), (uint16_t)(r * p.conv_dil));
-            } else if (AMODE == AMODE_STEM16) {
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), SM::kStageBytes);
+              if (AMODE == AMODE_IM2COL) {
+                tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
+                                   im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
+                                   (uint16_t)(tap_s * p.conv_dil), (uint16_t)(tap_r * p.conv_dil));
+              } else if (AMODE == AMODE_STEM16) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                int tap = kb * 4 + t;
-                if (tap >= p.conv_taps) tap = 0;  // padding tap: its weights are zero (OOB in B's tap dimension)
-                const int a = tap / p.conv_kw, b = tap - a * p.conv_kw;
-                tma_load_im2col_4d(sA + stage * SM::kABytes + t * 4096, &tmA, full_bar(stage), 0, im_w, im_h, im_n,
-                                   (uint16_t)b, (uint16_t)a);
+                for (int t = 0; t < 4; ++t) {
+                  int tap = kb * 4 + t;
+                  if (tap >= p.conv_taps) tap = 0;  // padding tap: its weights are zero (OOB in B's tap dimension)
+                  const int a = tap / p.conv_kw, b = tap - a * p.conv_kw;
+                  tma_load_im2col_4d(sA + stage * SM::kABytes + t * 4096, &tmA, full_bar(stage), 0, im_w, im_h, im_n,
+                                     (uint16_t)b, (uint16_t)a);
+                }
+              } else {
+                tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
               }
-            } else {
-              tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
+              if (AMODE == AMODE_STEM16)
+                tma_load_3d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), 0, nb * BLOCK_N, kb * 4);
+              else
+                tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
             }
-            if (AMODE == AMODE_STEM16)
-              tma_load_3d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), 0, nb * BLOCK_N, kb * 4);
-            else
-              tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
+            __syncwarp();
+            if (AMODE == AMODE_IM2COL) {
+              if (++cb == p.conv_cblocks) {
+                cb = 0;
+                if (++tap_s == p.conv_kw) {
+                  tap_s = 0;
+                  ++tap_r;
+                }
+              }
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -200,9 +210,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc(TR::kFmt, 128, BLOCK_N);
+      const uint64_t a_desc0 = umma_desc_sw128(sA), b_desc0 = umma_desc_sw128(sB);
+      const uint64_t a_desc0_sw32 = umma_desc_sw32(sA), b_desc0_sw32 = umma_desc_sw32(sB);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile = 0;
@@ -217,28 +229,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            if constexpr (AMODE == AMODE_STEM16) {
+            // the descriptor's address field (16-byte units) is advanced by adds
+            const uint32_t a_off = (uint32_t)(stage * SM::kABytes) >> 4, b_off = (uint32_t)(stage * SM::kBBytes) >> 4;
+            if (elect_one()) {
+              if constexpr (AMODE == AMODE_STEM16) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // one tap (16 channels = 32 bytes = one K-step) per MMA
-                const uint64_t adesc = umma_desc_sw32(sA + stage * SM::kABytes + k * 4096);
-                const uint64_t bdesc = umma_desc_sw32(sB + stage * SM::kBBytes + k * (BLOCK_N * 32));
-                umma<TR::kTF32>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
-              }
-            } else {
-              const uint64_t adesc = umma_desc_sw128(sA + stage * SM::kABytes);
-              const uint64_t bdesc = umma_desc_sw128(sB + stage * SM::kBBytes);
+                for (int k = 0; k < 4; ++k)  // one tap (16 channels = 32 bytes = one K-step) per MMA
+                  umma<TR::kTF32>(d_tmem, a_desc0_sw32 + a_off + (uint32_t)(k * 4096 >> 4),
+                                  b_desc0_sw32 + b_off + (uint32_t)(k * BLOCK_N * 32 >> 4), idesc, (kb | k) != 0);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte swizzle row
-                umma<TR::kTF32>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte swizzle row
+                  umma<TR::kTF32>(d_tmem, a_desc0 + a_off + 2u * k, b_desc0 + b_off + 2u * k, idesc, (kb | k) != 0);
               }
+              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+              if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
             }
-            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         }
       }
     }

@@ -104,6 +104,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with the whole
+// warp in uniform control flow and guard only the issuing instructions with this predicate: loop counters, barrier
+// addresses and descriptors then live in uniform registers and ptxas emits back-to-back UTCHMMA / UTMALDG.  Wrapping
+// the loops in `if (lane == 0)` instead makes every such instruction a per-lane ELECT/BRA.U.ANY loop fed by R2UR moves,
+// ~65 SASS instructions per 4-MMA k-block - slower than the 4 MMAs themselves for N <= 128.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler can prove warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // D[tmem] (+)= A[smem desc] * B[smem desc];  kind::f16 covers bf16/fp16 inputs, kind::tf32 fp32 inputs read as tf32.
 template <bool TF32>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {

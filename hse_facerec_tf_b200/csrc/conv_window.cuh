@@ -56,6 +56,8 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
 constexpr int kWinStages = 3;
 
 // dynamic smem: [1 KB align][weights w_bytes][kWinStages x window win_bytes (1 KB-rounded)][4 x 16 KB staging][barriers]
+// TH x TW taps with KS K=16 steps each known at compile time unroll the MMA issue completely (TH = 0: runtime loops).
+template <int TH, int TW, int KS>
 __global__ void __launch_bounds__(384, 1)
 conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmD, const WinParams p, const int w_bytes, const int win_stride) {
@@ -166,6 +168,19 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint64_t a_row = a_desc0 + (uint64_t)((uint32_t)(stage * win_stride) >> 4);
         uint64_t bd = b_desc0;
         uint32_t first = 0;
+        if constexpr (TH > 0) {
+          // independent descriptor offsets, no loop-carried chain through the (slow) uniform datapath
+#pragma unroll
+          for (int r = 0; r < TH; ++r)
+#pragma unroll
+            for (int s = 0; s < TW; ++s)
+#pragma unroll
+              for (int j = 0; j < KS; ++j) {
+                const int i = (r * TW + s) * KS + j;
+                umma<false>(d_tmem, a_row + (uint64_t)(r * a_row_step + s * a_col_step + j * a_k_step),
+                            bd + (uint64_t)(i * b_k_step), idesc, i != 0);
+              }
+        } else
         for (int r = 0; r < p.taps_h; ++r, a_row += a_row_step) {
           uint64_t a_tap = a_row;
           for (int s = 0; s < p.taps_w; ++s, a_tap += a_col_step) {

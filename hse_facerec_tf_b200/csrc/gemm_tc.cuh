@@ -63,10 +63,12 @@ struct GemmTraits<float> {
   static constexpr int BK = 32;
 };
 
-template <int BLOCK_N, int EPI>
+// CTAS = 2: CTA pair (cta_group::2) - the tile is 256 rows x BLOCK_N, each CTA stages its own 128 rows of A and
+// BLOCK_N / 2 rows of B per k-block, so a k-block costs each SM 2/3 (BLOCK_N = 256) of the L2->SM bytes of the 1-CTA tile.
+template <int BLOCK_N, int EPI, int CTAS = 1>
 struct GemmSmem {
   static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kBBytes = BLOCK_N / CTAS * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = (EPI == EPI_STORE) ? 4 * 128 * 128 : 2 * BLOCK_N * 4;  // 2 warpgroups x 2 buffers
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kEpiBytes;
@@ -75,12 +77,12 @@ struct GemmSmem {
   static constexpr int kTotal = 1024 + kStages * kStageBytes + kEpiBytes + 256;
 };
 
-template <typename T, int BLOCK_N, int EPI, int AMODE>
+template <typename T, int BLOCK_N, int EPI, int AMODE, int CTAS = 1>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using TR = GemmTraits<T>;
-  using SM = GemmSmem<BLOCK_N, EPI>;
+  using SM = GemmSmem<BLOCK_N, EPI, CTAS>;
   constexpr int STAGES = SM::kStages;
   constexpr int BK = TR::BK;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
@@ -103,6 +105,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tempty barriers both CTAs signal).  Work units are
+  // strided over clusters; the CTA of rank r owns m block  CTAS * (unit's m block) + r.
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const int unit0 = (int)blockIdx.x / CTAS, unit_stride = (int)gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -115,14 +121,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 4 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 4; ++s) mbar_init(rfull_bar(s), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 2) tmem_alloc<TMEM_COLS, CTAS>(smem_u32(tmem_slot));
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();  // the next kernel may run its prologue now ...
@@ -137,11 +144,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // KNN: m fastest (all CTAs sweep the same gallery range while it is L2-resident).
   auto decode = [&](int u, int& mb, int& nb0, int& nbn) {
     if (EPI == EPI_STORE) {
-      mb = u / units_n;
+      mb = (u / units_n) * CTAS + (int)cta_rank;
       nb0 = u % units_n;
       nbn = 1;
     } else {
-      mb = u % p.num_m_blocks;
+      mb = (u % p.num_m_blocks) * CTAS + (int)cta_rank;
       int sp = u / p.num_m_blocks;
       nb0 = sp * p.n_blocks_per_unit;
       nbn = min(p.n_blocks_per_unit, p.num_n_blocks - nb0);
@@ -153,7 +160,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      // pair: completion bytes of both CTAs' loads land on the leader's barrier
+      const uint32_t full_bar0 = (CTAS == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         int im_n = 0, im_h = 0, im_w = 0;
@@ -169,8 +178,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), SM::kStageBytes);
-              if (AMODE == AMODE_IM2COL) {
+              const uint32_t fb = full_bar0 + 8u * stage;
+              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), SM::kStageBytes * CTAS);
+              if constexpr (CTAS == 2) {
+                static_assert(CTAS == 1 || AMODE != AMODE_STEM16, "pair mode: 2-D and im2col A operands only");
+                if (AMODE == AMODE_IM2COL)
+                  tma_load_im2col_4d_pair(sA + stage * SM::kABytes, &tmA, fb, cb * BK,
+                                          im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
+                                          (uint16_t)(tap_s * p.conv_dil), (uint16_t)(tap_r * p.conv_dil));
+                else
+                  tma_load_2d_pair(sA + stage * SM::kABytes, &tmA, fb, kb * BK, mb * 128);
+                // this CTA's half of the tile's B rows
+                tma_load_2d_pair(sB + stage * SM::kBBytes, &tmB, fb, kb * BK,
+                                 nb * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+              } else if (AMODE == AMODE_IM2COL) {
                 tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
                                    im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
                                    (uint16_t)(tap_s * p.conv_dil), (uint16_t)(tap_r * p.conv_dil));
@@ -186,9 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
                 tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
               }
-              if (AMODE == AMODE_STEM16)
+              if (CTAS == 1 && AMODE == AMODE_STEM16)
                 tma_load_3d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), 0, nb * BLOCK_N, kb * 4);
-              else
+              else if (CTAS == 1)
                 tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
             }
             __syncwarp();
@@ -208,17 +229,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if constexpr (CTAS == 2) {
+        // tail: every slot-free arrival the leader's commits multicast into this CTA has landed before it may exit
+        for (int i = 0; i < STAGES; ++i) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
-    {
-      constexpr uint32_t idesc = umma_idesc(TR::kFmt, 128, BLOCK_N);
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(TR::kFmt, 128 * CTAS, BLOCK_N);
       const uint64_t a_desc0 = umma_desc_sw128(sA), b_desc0 = umma_desc_sw128(sB);
       const uint64_t a_desc0_sw32 = umma_desc_sw32(sA), b_desc0_sw32 = umma_desc_sw32(sB);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         for (int nb = nb0; nb < nb0 + nbn; ++nb, ++tile) {
@@ -237,13 +268,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < 4; ++k)  // one tap (16 channels = 32 bytes = one K-step) per MMA
                   umma<TR::kTF32>(d_tmem, a_desc0_sw32 + a_off + (uint32_t)(k * 4096 >> 4),
                                   b_desc0_sw32 + b_off + (uint32_t)(k * BLOCK_N * 32 >> 4), idesc, (kb | k) != 0);
+              } else if constexpr (CTAS == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_pair<TR::kTF32>(d_tmem, a_desc0 + a_off + 2u * k, b_desc0 + b_off + 2u * k, idesc, (kb | k) != 0);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte swizzle row
                   umma<TR::kTF32>(d_tmem, a_desc0 + a_off + 2u * k, b_desc0 + b_off + 2u * k, idesc, (kb | k) != 0);
               }
-              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-              if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+              if constexpr (CTAS == 2) {
+                umma_commit_pair(empty_bar(stage));  // frees the slot in both CTAs
+                if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as));
+              } else {
+                umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                if (kb == num_kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+              }
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -277,9 +317,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int pf_t = g, pf_c = 0;           // leader only: next (local tile, chunk) whose residual has not been requested
       uint32_t pf_ctr = 0;
       auto prefetch_next = [&]() {      // leader only
-        const int u2 = blockIdx.x + pf_t * gridDim.x;
+        const int u2 = unit0 + pf_t * unit_stride;
         if (u2 >= p.num_units) return;
-        const int mb2 = u2 / units_n2, nb2 = u2 % units_n2;
+        const int mb2 = (u2 / units_n2) * CTAS + (int)cta_rank, nb2 = u2 % units_n2;
         const int n2 = nb2 * BLOCK_N + pf_c * CH_ELEMS;
         const uint32_t b2 = pf_ctr & 1;
         mbar_expect_tx(rfull_bar(g * 2 + b2), 16384);
@@ -291,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       if (use_res && leader) prefetch_next();
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++tile) {
+      for (int u = unit0; u < p.num_units; u += unit_stride, ++tile) {
         if ((tile & 1) != (uint32_t)g) continue;
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
@@ -405,13 +445,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));  // the leader CTA's barrier
+          else mbar_arrive(tempty_bar(as));
+        }
       }
       if (leader) tma_store_wait_all();
     } else {
       // ---------------------------------------------------------------- EPI_KNN
       float* gn = reinterpret_cast<float*>(sEpi_gen) + g * BLOCK_N;  // this warpgroup's gallery-norm slice
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         float b1 = INFINITY, b2 = INFINITY;
@@ -453,7 +496,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) {
+            if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+            else mbar_arrive(tempty_bar(as));
+          }
         }
         const int m = mb * 128 + row;
         if (m < p.M) {
@@ -470,8 +516,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if constexpr (CTAS == 2) cluster_sync_all();  // neither CTA's shared memory / TMEM goes away while the peer uses it
+  else __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS, CTAS>(tmem_base);
 }
 
 }  // namespace hfr

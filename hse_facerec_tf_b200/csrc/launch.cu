@@ -31,20 +31,37 @@ static bool pdl_enabled() {
   static const bool on = getenv("HFR_NO_PDL") == nullptr;
   return on;
 }
+// cluster_x > 1: launch as thread-block clusters of that many CTAs along x (the grid must be a multiple of it)
 template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+static void launch_pdl_cluster(void (*kern)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                               Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   cuda_check(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...), "cudaLaunchKernelEx");
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  launch_pdl_cluster(kern, 1, grid, block, smem, s, std::forward<Args>(args)...);
 }
 
 int device_sm_count(int device) {
@@ -194,27 +211,49 @@ void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM (tcgen05)
-template <typename T, int BLOCK_N, int EPI, int AMODE>
+// CTAS = 2: CTA-pair tiles (256 rows); p.num_units / p.num_m_blocks then count pairs, and the grid is two CTAs per unit.
+template <typename T, int BLOCK_N, int EPI, int AMODE, int CTAS = 1>
 static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tR,
                              const GemmParams& p, int device, cudaStream_t s) {
-  using SM = GemmSmem<BLOCK_N, EPI>;
-  auto kern = gemm_tc_kernel<T, BLOCK_N, EPI, AMODE>;
+  using SM = GemmSmem<BLOCK_N, EPI, CTAS>;
+  auto kern = gemm_tc_kernel<T, BLOCK_N, EPI, AMODE, CTAS>;
   static std::atomic<bool> configured[64];
   if (!configured[device].load()) {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal),
                "cudaFuncSetAttribute(gemm smem)");
     configured[device].store(true);
   }
-  int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
+  const int slots = device_sm_count(device) / CTAS;  // concurrently resident units
+  int grid = (p.num_units < slots ? p.num_units : slots) * CTAS;
   if (grid < 1) return;
-  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB, tD, tR, p);
+  launch_pdl_cluster(kern, CTAS, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB, tD, tR, p);
   HFR_LAUNCH_CHECK("gemm_tc");
+}
+
+// CTA pairs halve the B (weight) bytes every SM pulls from L2 per k-block.  Measured per layer on ResNet-50 (B = 256):
+// the implicit-GEMM convolutions (long K, A re-read per tap from L2) gain 8-12 %, 1x1 layers with K >= 1024 gain 3-8 %,
+// short-K 1x1 layers - HBM/epilogue-bound, where coupling two CTAs' epilogues only removes slack - lose 5-15 %.
+// Used when the output width splits into 256- or 128-column pair tiles and there is at least one full wave of pairs.
+static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool is_conv) {
+  static const char* mode = getenv("HFR_PAIR");  // "0": never, "1": whenever the shape allows, unset: measured policy
+  if (mode && mode[0] == '0') return 0;
+  if (!(mode && mode[0] == '1') && !is_conv && K < 1024) return 0;
+  const bool need_even_m_blocks = is_conv;  // im2col base pixels past the last image are not loaded
+  const int64_t mb = (M + 127) / 128;
+  if (need_even_m_blocks && (mb & 1)) return 0;
+  const int64_t pairs = (mb + 1) / 2;
+  const int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 0;
+  if (bn == 0) return 0;
+  if (pairs * (N / bn) < sms / 2) return 0;
+  return bn;
 }
 
 static int pick_block_n(int64_t M, int N, int sms) {
   const int64_t mb = (M + 127) / 128;
   const int cands[3] = {256, 128, 64};
+  static const int cap = getenv("HFR_BLOCK_N_MAX") ? atoi(getenv("HFR_BLOCK_N_MAX")) : 256;  // tuning experiments
   for (int c : cands) {
+    if (c > cap && c != 64) continue;
     if (c > N && c != 64) continue;
     if (N % c != 0 && c != 64) continue;
     if (mb * ((N + c - 1) / c) >= sms) return c;
@@ -225,10 +264,20 @@ static int pick_block_n(int64_t M, int N, int sms) {
 template <typename T, int AMODE>
 static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, GemmParams p, int64_t M, int N, int K,
                               int prec, int device, cudaStream_t s) {
-  const int bn = pick_block_n(M, N, device_sm_count(device));
-  CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
   CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
   CUtensorMap tR = p.residual ? make_tmap_2d(p.residual, prec, (uint64_t)M, (uint64_t)N, 128) : tD;
+  if (const int pbn = pick_pair_block_n(M, N, K, device_sm_count(device), AMODE != AMODE_2D)) {
+    CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)pbn / 2);  // each CTA loads half the rows
+    p.num_m_blocks = (int)((M + 255) / 256);
+    p.num_n_blocks = N / pbn;
+    p.n_blocks_per_unit = 1;
+    p.num_units = p.num_m_blocks * p.num_n_blocks;
+    if (pbn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, p, device, s);
+    else launch_gemm_inst<T, 128, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, p, device, s);
+    return;
+  }
+  const int bn = pick_block_n(M, N, device_sm_count(device));
+  CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
   p.num_m_blocks = (int)((M + 127) / 128);
   p.num_n_blocks = (N + bn - 1) / bn;
   p.n_blocks_per_unit = 1;
@@ -375,6 +424,18 @@ bool conv_window_fits(int cin, int kh, int kw) {
   window_smem(cin, kh, kw, &wb, &wn, &ws, &tot);
   return tot <= 227 * 1024;
 }
+template <int TH, int TW, int KS>
+static void launch_window_inst(int grid, int total, int device, cudaStream_t s, const CUtensorMap& tX, const CUtensorMap& tW,
+                               const CUtensorMap& tD, const WinParams& p, int w_bytes, int win_stride) {
+  auto kern = conv_window_kernel<TH, TW, KS>;
+  static std::atomic<bool> configured[64];  // per instantiation
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+               "cudaFuncSetAttribute(window smem)");
+    configured[device].store(true);
+  }
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)total, s, tX, tW, tD, p, w_bytes, win_stride);
+}
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   if (a.cout > 64 || a.cout % 32 || !conv_window_fits(a.cin, a.kh, a.kw)) throw Error(-5, "window conv: unsupported shape");
   int w_bytes, win_bytes, win_stride, total;
@@ -417,15 +478,14 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   p.plane_pitch = shifted ? wh * 128 : a.plane_major ? plane_px : (plane_px + 127) / 128 * 128;
   p.shifted = shifted;
   p.copy_pitch = planes * wh * 128;
-  static std::atomic<bool> configured[64];
-  if (!configured[device].load()) {
-    cuda_check(cudaFuncSetAttribute(conv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-               "cudaFuncSetAttribute(window smem)");
-    configured[device].store(true);
-  }
   const int grid = p.num_tiles < device_sm_count(device) ? p.num_tiles : device_sm_count(device);
   if (grid < 1) return;
-  launch_pdl(conv_window_kernel, dim3(grid), dim3(384), (size_t)total, s, tX, tW, tD, p, w_bytes, win_stride);
+  // fully unrolled MMA issue for the shapes the networks use: stem after space-to-depth (4x4 taps x 16 channels),
+  // 3x3 over 64 and 32 channels
+  if (a.kh == 4 && a.kw == 4 && planes == 2) launch_window_inst<4, 4, 1>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
+  else if (a.kh == 3 && a.kw == 3 && planes == 8) launch_window_inst<3, 3, 4>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
+  else if (a.kh == 3 && a.kw == 3 && planes == 4) launch_window_inst<3, 3, 2>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
+  else launch_window_inst<0, 0, 0>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
   HFR_LAUNCH_CHECK("conv_window");
 }
 

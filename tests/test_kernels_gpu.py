@@ -33,6 +33,8 @@ def tf32_round(t):
 GEMM_SHAPES = [
     (128, 64, 32), (128, 64, 64), (300, 128, 256), (1000, 256, 1024), (4096, 512, 512), (12544, 64, 32),
     (2304, 1024, 512), (130, 1024, 1024), (77, 128, 128), (50176, 128, 64),
+    # large enough for the CTA-pair (cta_group::2) tiles: odd m-block count with a ragged tail, 256- and 128-wide pair tiles
+    (20000, 256, 512), (33000, 512, 192), (9600, 1024, 2048), (40100, 384, 64),
 ]
 
 
@@ -186,6 +188,7 @@ def test_stem_conv_tensor_core(case, flags):
 CONV_CASES = [  # (B, H, W, cin, cout, k, stride)
     (2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1), (5, 7, 7, 512, 512, 3, 1),
     (1, 9, 11, 64, 128, 3, 1), (2, 16, 16, 64, 64, 3, 2),
+    (128, 14, 14, 256, 256, 3, 1), (32, 28, 28, 128, 128, 3, 1), (40, 28, 28, 64, 256, 3, 2),  # CTA-pair tiles
 ]
 
 

@@ -222,10 +222,49 @@ struct hfr_model {
     return (b + 255) / 256 * 256;
   }
 
+  // Strided 1x1 convolutions: the plan states them as gather (L_SUBSAMPLE) + GEMM.  On the tensor-core path the GEMM's A
+  // operand can be fetched by an im2col tensor map with a traversal stride instead, straight from the un-gathered tensor:
+  // gather_of[li] >= 0 names the L_SUBSAMPLE layer a pointwise layer li bypasses; a gather whose consumers all bypass it
+  // is skipped.  Off when every activation has to exist (keep_all) or in fp32 (SIMT GEMM has no im2col operand).
+  std::vector<int> gather_of;
+  std::vector<char> skip_layer;
+  void plan_gather_bypass() {
+    const size_t n = plan.layers.size();
+    gather_of.assign(n, -1);
+    skip_layer.assign(n, 0);
+    if (keep_all || precision == HFR_FP32 || getenv("HFR_NO_STRIDED_GEMM")) return;
+    const int bk = 128 / (int)elt_size(precision);
+    for (size_t si = 0; si < n; ++si) {
+      const Layer& S = plan.layers[si];
+      if (S.kind != L_SUBSAMPLE || S.cin % bk) continue;
+      bool all = true, any = false;
+      for (size_t li = 0; li < n; ++li) {
+        const Layer& L = plan.layers[li];
+        if (L.in2 == S.out) all = false;
+        if (L.in != S.out) continue;
+        if (L.kind == L_PW && li > si) any = true; else all = false;
+      }
+      for (int o : plan.outputs) if (o == S.out) all = false;
+      if (!all || !any) continue;
+      skip_layer[si] = 1;
+      for (size_t li = si + 1; li < n; ++li)
+        if (plan.layers[li].in == S.out) gather_of[li] = (int)si;
+    }
+  }
+
   void plan_arena() {
     const int nv = (int)plan.values.size();
     val_off.assign((size_t)nv, 0);
     val_bytes.assign((size_t)nv, 0);
+    plan_gather_bypass();
+    // a bypassing layer reads the gather's INPUT: that value lives until its last bypassing reader
+    std::vector<int> last_use((size_t)nv);
+    for (int v = 0; v < nv; ++v) last_use[(size_t)v] = plan.values[(size_t)v].last_use;
+    for (size_t li = 0; li < plan.layers.size(); ++li)
+      if (gather_of[li] >= 0) {
+        const int src = plan.layers[(size_t)gather_of[li]].in;
+        if (src > 0 && last_use[(size_t)src] < (int)li) last_use[(size_t)src] = (int)li;
+      }
     struct Block { size_t off, size; };
     std::vector<Block> free_list;
     size_t top = 0;
@@ -257,6 +296,10 @@ struct hfr_model {
     };
     for (int li = 0; li < (int)plan.layers.size(); ++li) {
       const Layer& L = plan.layers[(size_t)li];
+      if (skip_layer[(size_t)li]) {  // never materialised; its input may end its life here unless a bypassing layer reads it
+        if (L.in > 0 && last_use[(size_t)L.in] == li) release(val_off[(size_t)L.in], val_bytes[(size_t)L.in]);
+        continue;
+      }
       val_bytes[(size_t)L.out] = value_image_bytes(L.out);
       val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
       if (keep_all) continue;
@@ -264,13 +307,14 @@ struct hfr_model {
       // stay allocated until the pair's output has its own block
       if (fused_pair((size_t)li)) continue;
       int ins[3] = {L.in, L.in2, -1};
+      if (gather_of[(size_t)li] >= 0) ins[0] = plan.layers[(size_t)gather_of[(size_t)li]].in;
       if (li > 0 && fused_pair((size_t)li - 1)) ins[2] = plan.layers[(size_t)li - 1].in;
       for (int v : ins) {
         if (v <= 0) continue;  // value 0 is the caller's input
-        const int lu = plan.values[(size_t)v].last_use;
+        const int lu = last_use[(size_t)v];
         if (lu == li || (v == ins[2] && lu == li - 1)) release(val_off[(size_t)v], val_bytes[(size_t)v]);
       }
-      if (plan.values[(size_t)L.out].last_use < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
+      if (last_use[(size_t)L.out] < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
     }
     per_image_bytes = top;
   }
@@ -284,7 +328,7 @@ struct hfr_model {
       if (!L.bias.empty()) d.bias = (float*)upload(L.bias.data(), L.bias.size() * 4);
       if (L.w.empty()) continue;
       const bool gemm_operand = (L.kind == L_PW || L.kind == L_CONV);
-      if (L.kind == L_CONV && precision == HFR_BF16 && getenv("HFR_WINDOW_CONV") != nullptr && L.stride == 1 && L.dil == 1 &&
+      if (L.kind == L_CONV && precision == HFR_BF16 && getenv("HFR_NO_WINDOW_CONV") == nullptr && L.stride == 1 && L.dil == 1 &&
           (L.cout == 64 || L.cout == 32) && conv_window_fits(L.cin, L.kh, L.kw)) {
         std::vector<uint16_t> hw = conv_window_layout(L.w.data(), L.cout, L.kh * L.kw, L.cin);
         d.w_win = upload(hw.data(), hw.size() * 2);
@@ -417,6 +461,17 @@ struct hfr_model {
           break;
         }
         case L_PW: {
+          if (gather_of[i] >= 0) {  // strided 1x1: im2col-gathered A operand, no materialised subsample
+            const Layer& S = plan.layers[(size_t)gather_of[i]];
+            ConvArgs a;
+            a.x = S.in == 0 ? x : vptr(S.in); a.w = d.w; a.bias = d.bias;
+            a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
+            a.y = out; a.B = batch; a.H = S.H; a.W = S.W; a.cin = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.cout = L.cout;
+            a.kh = 1; a.kw = 1; a.stride = S.stride; a.pad_t = 0; a.pad_l = 0; a.dil = 1;
+            a.act = act; a.round_tf32 = round_out;
+            launch_conv(a, prec, device, s);
+            break;
+          }
           GemmArgs a;
           a.a = in; a.b = d.w; a.bias = d.bias;
           a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
@@ -451,6 +506,7 @@ struct hfr_model {
           break;
         }
         case L_SUBSAMPLE:
+          if (skip_layer[i]) break;
           launch_subsample(in, out, batch, L.H, L.W, L.cin, L.Ho, L.Wo, L.stride, prec, s);
           break;
         case L_GAP:

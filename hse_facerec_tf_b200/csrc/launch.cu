@@ -234,11 +234,11 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
 // the implicit-GEMM convolutions (long K, A re-read per tap from L2) gain 8-12 %, 1x1 layers with K >= 1024 gain 3-8 %,
 // short-K 1x1 layers - HBM/epilogue-bound, where coupling two CTAs' epilogues only removes slack - lose 5-15 %.
 // Used when the output width splits into 256- or 128-column pair tiles and there is at least one full wave of pairs.
-static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool is_conv) {
+static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool im2col, bool multi_tap) {
   static const char* mode = getenv("HFR_PAIR");  // "0": never, "1": whenever the shape allows, unset: measured policy
   if (mode && mode[0] == '0') return 0;
-  if (!(mode && mode[0] == '1') && !is_conv && K < 1024) return 0;
-  const bool need_even_m_blocks = is_conv;  // im2col base pixels past the last image are not loaded
+  if (!(mode && mode[0] == '1') && !multi_tap && K < 1024) return 0;
+  const bool need_even_m_blocks = im2col;  // im2col base pixels past the last image are not loaded
   const int64_t mb = (M + 127) / 128;
   if (need_even_m_blocks && (mb & 1)) return 0;
   const int64_t pairs = (mb + 1) / 2;
@@ -248,10 +248,11 @@ static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool is_conv) {
   return bn;
 }
 
-static int pick_block_n(int64_t M, int N, int sms) {
+static int pick_block_n(int64_t M, int N, int sms, int widest) {
   const int64_t mb = (M + 127) / 128;
   const int cands[3] = {256, 128, 64};
-  static const int cap = getenv("HFR_BLOCK_N_MAX") ? atoi(getenv("HFR_BLOCK_N_MAX")) : 256;  // tuning experiments
+  static const int env_cap = getenv("HFR_BLOCK_N_MAX") ? atoi(getenv("HFR_BLOCK_N_MAX")) : 0;  // tuning experiments
+  const int cap = env_cap ? env_cap : widest;
   for (int c : cands) {
     if (c > cap && c != 64) continue;
     if (c > N && c != 64) continue;
@@ -266,7 +267,8 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
                               int prec, int device, cudaStream_t s) {
   CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
   CUtensorMap tR = p.residual ? make_tmap_2d(p.residual, prec, (uint64_t)M, (uint64_t)N, 128) : tD;
-  if (const int pbn = pick_pair_block_n(M, N, K, device_sm_count(device), AMODE != AMODE_2D)) {
+  if (const int pbn = pick_pair_block_n(M, N, K, device_sm_count(device), AMODE != AMODE_2D,
+                                        AMODE != AMODE_2D && p.conv_kw > 1)) {
     CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)pbn / 2);  // each CTA loads half the rows
     p.num_m_blocks = (int)((M + 255) / 256);
     p.num_n_blocks = N / pbn;
@@ -276,7 +278,9 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
     else launch_gemm_inst<T, 128, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, p, device, s);
     return;
   }
-  const int bn = pick_block_n(M, N, device_sm_count(device));
+  // 1x1 layers are HBM / latency bound: 128-column tiles (twice the units, five 32 KB stages in flight instead of three
+  // 48 KB ones) measured faster than 256-column ones on every ResNet-50 1x1 layer but two ties
+  const int bn = pick_block_n(M, N, device_sm_count(device), (AMODE == AMODE_2D || p.conv_kw == 1) ? 128 : 256);
   CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
   p.num_m_blocks = (int)((M + 127) / 128);
   p.num_n_blocks = (N + bn - 1) / bn;
@@ -548,6 +552,13 @@ void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s) {
   p.pad_t = a.pad_t; p.pad_l = a.pad_l; p.explicit_zero = a.explicit_zero;
   const int vn = prec == PREC_BF16 ? 8 : 4;
   if (a.C % vn) throw Error(-1, "maxpool: channels must be a multiple of the 16-byte vector");
+  if (prec == PREC_BF16 && a.k == 3 && a.stride == 2) {
+    const long long pairs = (long long)a.B * a.Ho * ((a.Wo + 1) / 2) * (a.C / 8);
+    launch_pdl(maxpool3x3s2_bf16_kernel, dim3(grid_for(pairs, 256)), dim3(256), 0, s, (const __nv_bfloat16*)a.x,
+               (__nv_bfloat16*)a.y, p);
+    HFR_LAUNCH_CHECK("maxpool3x3s2");
+    return;
+  }
   const long long total = (long long)a.B * a.Ho * a.Wo * (a.C / vn);
   if (prec == PREC_BF16)
     launch_pdl(maxpool_kernel<__nv_bfloat16>, dim3(grid_for(total, 256)), dim3(256), 0, s, (const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, p);
@@ -671,6 +682,18 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
   p.num_units = p.num_m_blocks * a.splits;
   p.gnorm = a.gnorm; p.part_score = a.part_score; p.part_idx = a.part_idx;
   CUtensorMap tA = make_tmap_2d(a.q, prec, (uint64_t)a.nq, (uint64_t)a.d, 128);
+  // CTA pairs (256 query rows x 256 gallery rows per tile, each CTA stages half of the gallery rows): fewer shared-memory
+  // and L2 bytes per flop; used when there is at least one wave of pair units
+  static const char* pair_mode = getenv("HFR_PAIR");
+  const int64_t pairs = (a.nq + 255) / 256;
+  if (!(pair_mode && pair_mode[0] == '0') && pairs * a.splits >= device_sm_count(device) / 2) {
+    p.num_m_blocks = (int)pairs;
+    p.num_units = p.num_m_blocks * a.splits;
+    CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 128);
+    if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);
+    else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);
+    return;
+  }
   CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 256);
   if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);
   else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);

@@ -267,13 +267,21 @@ def test_fused_dw_pw_block(B, H, W, cin, cout):
 
 @pytest.mark.parametrize("prec", [1, 2])
 @pytest.mark.parametrize("explicit_zero", [0, 1])
-def test_maxpool(prec, explicit_zero):
+@pytest.mark.parametrize("shape", [(3, 112, 112, 64), (2, 13, 13, 64), (2, 9, 14, 32), (1, 5, 3, 128)])
+def test_maxpool(prec, explicit_zero, shape):
+    """3x3 / stride 2 SAME pooling (pad_before = total // 2): even sizes pad bottom/right only, odd sizes pad both
+    sides and give an odd output width (the paired-output bf16 kernel's ragged last column)."""
     dt = TDT[prec]
-    x = (torch.randn(3, 112, 112, 64, generator=torch.Generator().manual_seed(4)) - 0.5).to(DEV).to(dt).contiguous()
-    y = torch.full((3, 56, 56, 64), float("nan"), dtype=dt, device=DEV)
-    check(lib.hfr_op_maxpool(x.data_ptr(), y.data_ptr(), 3, 112, 112, 64, 3, 2, 0, 0, 56, 56, explicit_zero, prec, 0, _stream()))
+    B, H, W, C = shape
+    ho, wo = -(-H // 2), -(-W // 2)
+    th, tw = max((ho - 1) * 2 + 3 - H, 0), max((wo - 1) * 2 + 3 - W, 0)
+    x = (torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(4)) - 0.5).to(DEV).to(dt).contiguous()
+    y = torch.full((B, ho, wo, C), float("nan"), dtype=dt, device=DEV)
+    check(lib.hfr_op_maxpool(x.data_ptr(), y.data_ptr(), B, H, W, C, 3, 2, th // 2, tw // 2, ho, wo, explicit_zero, prec, 0,
+                             _stream()))
     torch.cuda.synchronize()
-    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1), value=0.0 if explicit_zero else -float("inf"))
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2),
+               value=0.0 if explicit_zero else -float("inf"))
     ref = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
     assert torch.equal(y.float(), ref)
 

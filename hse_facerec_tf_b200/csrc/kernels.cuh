@@ -335,6 +335,159 @@ __global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant
   }
 }
 
+// Persistent, software-pipelined variant of the kernel above (the default): a producer warp keeps `stages` halo windows in
+// flight through a TMA ring while 16*VL compute threads drain them, so an SM holds stages x CTAs windows of loads
+// outstanding instead of one per resident CTA, tiles cost no CTA launch, and the per-CTA constants (this CTA's channel
+// block of weights and bias) are staged once: the launcher makes the grid a multiple of the channel-block count, so a
+// CTA's tiles  t = blockIdx.x + k * gridDim.x  all share  cb = blockIdx.x % cblocks.  VL (16-byte vectors per pixel) is a
+// template parameter: every shared-memory offset is an immediate.
+struct DwPipeParams {
+  int C, Ho, Wo, pad_t, pad_l, tiles_w, tiles_h, cblocks, act, round_tf32, stages, stage_bytes;
+  long long num_tiles;
+};
+
+template <typename T, int STRIDE, int VL>
+__global__ void __launch_bounds__(16 * VL + 32) dwconv3x3_pipe_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                      const float* __restrict__ w,     // [9][C]
+                                                                      const float* __restrict__ bias,  // [C]
+                                                                      T* __restrict__ y, const DwPipeParams p) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int CBE = VL * VN;                 // channels per tile
+  constexpr int NCOMP = 16 * VL;               // compute threads: 16 strips of 4 vertically adjacent outputs x VL vectors
+  constexpr int TWI = 7 * STRIDE + 3, THI = 7 * STRIDE + 3;
+  constexpr int NROWS = 3 * STRIDE + 3;        // input rows touched by 4 vertically adjacent outputs
+  constexpr int kMaxStages = 6;
+  extern __shared__ uint8_t dwp_smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages];
+  __shared__ __align__(16) float w_s[9 * CBE];
+  uint8_t* ring = dwp_smem_raw + ((128u - (smem_u32(dwp_smem_raw) & 127u)) & 127u);  // TMA destinations: 128-B aligned
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * kMaxStages;
+  const int warp = uniform_warp_idx();
+  const int cb = (int)(blockIdx.x % (unsigned)p.cblocks);
+  const int c0 = cb * CBE;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, NCOMP / 32);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 9 * CBE; i += blockDim.x) w_s[i] = __ldg(w + (size_t)(i / CBE) * p.C + c0 + i % CBE);
+  pdl_wait();       // loads of, and stores over, tensors of the predecessor only after it has completed
+  __syncthreads();
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  auto decode = [&](long long t, int& b, int& oy0, int& ox0) {
+    const long long sp = t / p.cblocks;  // t % cblocks == cb by construction
+    b = (int)(sp / tiles_per_img);
+    const int r = (int)(sp - (long long)b * tiles_per_img);
+    const int ty = r / p.tiles_w;
+    oy0 = ty * 8;
+    ox0 = (r - ty * p.tiles_w) * 8;
+  };
+  if (warp == NCOMP / 32) {
+    // ------------------------------------------------------------ producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int b, oy0, ox0;
+      decode(t, b, oy0, ox0);
+      mbar_wait(empty0 + 8u * stage, phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(full0 + 8u * stage, (uint32_t)(TWI * THI * CBE * sizeof(T)));
+        tma_load_4d(ring_u + (uint32_t)(stage * p.stage_bytes), &tmX, full0 + 8u * stage, c0, ox0 * STRIDE - p.pad_l,
+                    oy0 * STRIDE - p.pad_t, b);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ compute
+    const int v = threadIdx.x % VL;
+    const int strip = threadIdx.x / VL;     // 0..15
+    const int lx = strip & 7;               // output column within the tile
+    const int ly0 = (strip >> 3) * 4;       // first of this thread's 4 output rows
+    const int c = c0 + v * VN;
+    float bs[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bs[e] = __ldg(bias + c + e);
+    const float* wv = w_s + v * VN;
+    const int in_off = ((ly0 * STRIDE) * TWI + lx * STRIDE) * CBE + v * VN;  // elements
+    const size_t row_pitch = (size_t)p.Wo * p.C;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int b, oy0, ox0;
+      decode(t, b, oy0, ox0);
+      mbar_wait(full0 + 8u * stage, phase);
+      const T* xin = reinterpret_cast<const T*>(ring + (size_t)stage * p.stage_bytes) + in_off;
+      float acc[4][VN];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
+      // one filter column at a time: only 3 taps x VN weights are live
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        float wk[3][VN];
+#pragma unroll
+        for (int kr = 0; kr < 3; ++kr) {
+#pragma unroll
+          for (int q = 0; q < VN / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(wv + (kr * 3 + s) * CBE + 4 * q);
+            wk[kr][4 * q] = t4.x; wk[kr][4 * q + 1] = t4.y; wk[kr][4 * q + 2] = t4.z; wk[kr][4 * q + 3] = t4.w;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+          float xv[VN];
+          Vec16<T>::load(xin + (r * TWI + s) * CBE, xv);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int kr = r - o * STRIDE;  // filter row this input row hits for output o
+            if (kr >= 0 && kr < 3) {
+#pragma unroll
+              for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
+            }
+          }
+        }
+      }
+      // the window is consumed: hand the slot back before the (long-latency) stores
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty0 + 8u * stage);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+      const int ox = ox0 + lx, oy = oy0 + ly0;
+      if (ox < p.Wo) {
+        T* dst = y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          if (oy + o < p.Ho) {
+            if constexpr (sizeof(T) == 2) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2_act(acc[o][2 * e], acc[o][2 * e + 1], p.act);
+              *reinterpret_cast<uint4*>(dst + o * row_pitch) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            } else {
+              float ov[VN];
+#pragma unroll
+              for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
+              Vec16<T>::store(dst + o * row_pitch, ov);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------------------------
 // Max pooling (k x k, stride s) over NHWC, 16-byte channel vectors.  Out-of-range taps are skipped (TF SAME) unless
 // explicit_zero is set (TF Pad followed by a VALID MaxPool: the pad pixels are real zeros and take part in the max).

@@ -195,8 +195,64 @@ static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
   launch_pdl(kern, grid, dim3(16 * VL), smem, s, tm, a.w, a.bias, (T*)a.y, p);
   HFR_LAUNCH_CHECK("dwconv3x3");
 }
+// persistent pipelined kernel: grid = resident CTAs (a multiple of the channel-block count), stages sized to ~52 KB of
+// windows per CTA
+template <typename T, int STRIDE, int VL>
+static void launch_dw_pipe_t(const DwArgs& a, int prec, int device, cudaStream_t s) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int CBE = VL * VN;
+  constexpr int TWI = 7 * STRIDE + 3;
+  const int es = (int)sizeof(T);
+  if (a.C % CBE) throw Error(-1, "depthwise: channels must be a multiple of the channel block");
+  const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t strides[3] = {(uint64_t)a.C * es, (uint64_t)a.W * a.C * es, (uint64_t)a.H * a.W * a.C * es};
+  const uint32_t box[4] = {(uint32_t)CBE, (uint32_t)TWI, (uint32_t)TWI, 1};
+  CUtensorMap tm = make_tiled(a.x, prec, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  DwPipeParams p;
+  p.C = a.C; p.Ho = a.Ho; p.Wo = a.Wo; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
+  p.tiles_w = (a.Wo + 7) / 8;
+  p.tiles_h = (a.Ho + 7) / 8;
+  p.cblocks = a.C / CBE;
+  p.act = a.act; p.round_tf32 = a.round_tf32;
+  p.stage_bytes = (TWI * TWI * CBE * es + 127) / 128 * 128;
+  p.stages = (52 * 1024) / p.stage_bytes;
+  if (p.stages < 2) p.stages = 2;
+  if (p.stages > 6) p.stages = 6;
+  p.num_tiles = (long long)a.B * p.tiles_w * p.tiles_h * p.cblocks;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+  auto kern = dwconv3x3_pipe_kernel<T, STRIDE, VL>;
+  static std::atomic<int> ctas_per_sm[64];  // per instantiation; the stage count is a function of the instantiation only
+  if (ctas_per_sm[device].load() == 0) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dw smem attribute");
+    int occ = 0;
+    cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 16 * VL + 32, smem), "dw occupancy");
+    if (occ < 1) throw Error(-6, "depthwise: kernel does not fit on an SM");
+    ctas_per_sm[device].store(occ);
+  }
+  long long grid = (long long)device_sm_count(device) * ctas_per_sm[device].load();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  grid = grid / p.cblocks * p.cblocks;      // every CTA keeps one channel block
+  if (grid < p.cblocks) grid = p.cblocks;
+  launch_pdl(kern, dim3((unsigned)grid), dim3(16 * VL + 32), smem, s, tm, a.w, a.bias, (T*)a.y, p);
+  HFR_LAUNCH_CHECK("dwconv3x3_pipe");
+}
+
 void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
   if (a.B > 65535) throw Error(-1, "depthwise: batch too large for one launch");
+  if (getenv("HFR_DW_ONESHOT") == nullptr && (a.stride == 1 || a.stride == 2)) {
+    int device = 0;
+    cuda_check(cudaGetDevice(&device), "cudaGetDevice");
+    const int es = prec == PREC_BF16 ? 2 : 4;
+    int VL = (a.C * es) / 16;
+    if (VL > 8) VL = 8;
+    if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
+#define HFR_DW_PIPE(T, S) \
+    do { if (VL == 8) launch_dw_pipe_t<T, S, 8>(a, prec, device, s); else launch_dw_pipe_t<T, S, 4>(a, prec, device, s); } while (0)
+    if (prec == PREC_BF16) { if (a.stride == 1) HFR_DW_PIPE(__nv_bfloat16, 1); else HFR_DW_PIPE(__nv_bfloat16, 2); }
+    else                   { if (a.stride == 1) HFR_DW_PIPE(float, 1); else HFR_DW_PIPE(float, 2); }
+#undef HFR_DW_PIPE
+    return;
+  }
   // 16x8-pixel tiles (TILE_H = 16) were measured 40 % slower than 8x8 on B200 (fewer, longer-running CTAs): kept only
   // as a template option
   const bool tall = getenv("HFR_DW_TALL") != nullptr && a.Ho > 8;

@@ -188,18 +188,40 @@ def bench_network(args, rank, world, dev):
         clocks = sampler.stop()
 
         # ---- e2e: pinned host batch -> H2D -> run -> D2H of the result, through the host-buffer C-ABI call
-        hx = [torch.from_numpy(synth_images(batch, size, 5000 + 1000 * rank + i)).pin_memory() for i in range(2)]
-        houts = [np.empty((batch, d), np.float32) for d in model.out_dims]
-        for i in range(3):
-            model.forward_host(hx[i % 2].numpy(), outs=houts, graph=True, **kw)
+        # The streaming form of the call (hfr_model_submit_host / hfr_model_wait_host, two batches in flight): every
+        # step's input still travels pinned host -> device and its result device -> pinned host inside the timed region,
+        # but step i+1's upload and step i-1's download overlap step i's compute.
+        depth = int(os.environ.get("HFR_BENCH_E2E_DEPTH", "2"))
+        hx = [torch.from_numpy(synth_images(batch, size, 5000 + 1000 * rank + i)).pin_memory() for i in range(depth)]
+        houts = [[torch.empty((batch, d), dtype=torch.float32).pin_memory().numpy() for d in model.out_dims]
+                 for _ in range(depth)]
+
+        hxn = [h.numpy() for h in hx]
+        host_s = [0.0, 0.0]  # seconds the host spent inside submit / wait (reported on stderr)
+
+        def e2e_run(n):
+            for i in range(n):
+                ta = time.perf_counter()
+                if i >= depth:
+                    model.wait_host(i % depth)
+                tb = time.perf_counter()
+                model.submit_host(i % depth, hxn[i % depth], houts[i % depth], graph=True, **kw)
+                host_s[0] += time.perf_counter() - tb
+                host_s[1] += tb - ta
+            for sl in range(depth):
+                model.wait_host(sl)
+
+        e2e_run(4)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            model.forward_host(hx[i % 2].numpy(), outs=houts, graph=True, **kw)
+        host_s[0] = host_s[1] = 0.0
+        e2e_run(args.steps)
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
+        print(f"[e2e] depth {depth}: {e2e_s / args.steps * 1e3:.3f} ms/step; host in submit {host_s[0] / args.steps * 1e3:.3f} ms, "
+              f"in wait {host_s[1] / args.steps * 1e3:.3f} ms per step", file=sys.stderr)
 
         # ---- per-kernel durations (CUDA events around every layer launch, eager, same stream)
         model.layer_timing(True)

@@ -23,6 +23,8 @@ SIGNATURES = {
     "hfr_model_layer_weights": (_i64, [_vp, _i, _vp, _i64, _vp, _i64]),
     "hfr_model_forward": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_vp), _vp]),
     "hfr_model_forward_host": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_vp), _vp]),
+    "hfr_model_submit_host": (_i, [_vp, _i, _vp, _i, _i, _i, C.POINTER(_vp), _vp]),
+    "hfr_model_wait_host": (_i, [_vp, _i]),
     "hfr_model_set_keep_activations": (_i, [_vp, _i]),
     "hfr_model_debug_layer": (_i64, [_vp, _i, _i, _vp, _vp]),
     "hfr_model_set_layer_timing": (_i, [_vp, _i]),

@@ -203,8 +203,41 @@ struct hfr_model {
   // host-buffer path staging
   DevBuf stage_in;
   std::vector<std::unique_ptr<DevBuf>> stage_out;
+  // hfr_model_submit_host / hfr_model_wait_host: kHostSlots batches in flight - the H2D copy of slot i+1 and the D2H copy
+  // of slot i-1 run on their own streams while slot i computes
+  static constexpr int kHostSlots = 4;
+  struct HostSlot {
+    DevBuf in;
+    std::vector<std::unique_ptr<DevBuf>> out;
+    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    bool busy = false;
+  };
+  HostSlot slots[kHostSlots];
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  void init_host_pipeline() {
+    if (copy_in) return;
+    cuda_check(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking), "cudaStreamCreate(copy in)");
+    cuda_check(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking), "cudaStreamCreate(copy out)");
+    for (HostSlot& h : slots) {
+      cuda_check(cudaEventCreateWithFlags(&h.in_done, cudaEventDisableTiming), "cudaEventCreate");
+      cuda_check(cudaEventCreateWithFlags(&h.comp_done, cudaEventDisableTiming), "cudaEventCreate");
+      cuda_check(cudaEventCreateWithFlags(&h.out_done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  void free_host_pipeline() {
+    if (!copy_in) return;
+    for (HostSlot& h : slots) {
+      cudaEventDestroy(h.in_done);
+      cudaEventDestroy(h.comp_done);
+      cudaEventDestroy(h.out_done);
+    }
+    cudaStreamDestroy(copy_in);
+    cudaStreamDestroy(copy_out);
+    copy_in = copy_out = nullptr;
+  }
 
   ~hfr_model() {
+    free_host_pipeline();
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto e : ev) cudaEventDestroy(e);
     for (auto& kv : stem_w2) cudaFree(kv.second.first);
@@ -716,6 +749,57 @@ int hfr_model_forward_host(hfr_model* m, const void* x_host, int in_dtype, int b
     for (size_t i = 0; i < no; ++i)
       cuda_check(cudaMemcpyAsync(outs_host[i], douts[i], obytes[i], cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(D2H)");
     cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  });
+}
+
+int hfr_model_submit_host(hfr_model* m, int slot, const void* x_host, int in_dtype, int batch, int flags,
+                          void* const* outs_host, void* stream) {
+  return guarded([&] {
+    if (!m || !x_host || !outs_host) throw Error(HFR_ERR_INVALID, "null argument");
+    if (m->device < 0) throw Error(HFR_ERR_STATE, "model was loaded host-only");
+    if (batch <= 0) throw Error(HFR_ERR_INVALID, "batch must be positive");
+    if (slot < 0 || slot >= hfr_model::kHostSlots) throw Error(HFR_ERR_INVALID, "slot out of range");
+    use_device(m->device);
+    m->init_host_pipeline();
+    hfr_model::HostSlot& h = m->slots[slot];
+    if (h.busy) throw Error(HFR_ERR_STATE, "slot still in flight: call hfr_model_wait_host(m, slot) first");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t in_bytes =
+        (size_t)batch * m->plan.in_h * m->plan.in_w * m->plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);
+    h.in.ensure(in_bytes);
+    const size_t no = m->plan.outputs.size();
+    for (size_t i = h.out.size(); i < no; ++i) h.out.emplace_back(new DevBuf());
+    std::vector<void*> douts(no);
+    std::vector<size_t> obytes(no);
+    for (size_t i = 0; i < no; ++i) {
+      const ValueInfo& v = m->plan.values[(size_t)m->plan.outputs[i]];
+      obytes[i] = (size_t)batch * v.H * v.W * v.C * 4;
+      h.out[i]->ensure(obytes[i]);
+      douts[i] = h.out[i]->p;
+    }
+    // the slot's previous use has been waited for (busy == false), so its buffers are free on every stream
+    cuda_check(cudaMemcpyAsync(h.in.p, x_host, in_bytes, cudaMemcpyHostToDevice, m->copy_in), "cudaMemcpyAsync(H2D)");
+    cuda_check(cudaEventRecord(h.in_done, m->copy_in), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(s, h.in_done, 0), "cudaStreamWaitEvent");
+    m->forward(h.in.p, in_dtype, batch, flags, douts.data(), s);
+    cuda_check(cudaEventRecord(h.comp_done, s), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(m->copy_out, h.comp_done, 0), "cudaStreamWaitEvent");
+    for (size_t i = 0; i < no; ++i)
+      cuda_check(cudaMemcpyAsync(outs_host[i], douts[i], obytes[i], cudaMemcpyDeviceToHost, m->copy_out),
+                 "cudaMemcpyAsync(D2H)");
+    cuda_check(cudaEventRecord(h.out_done, m->copy_out), "cudaEventRecord");
+    h.busy = true;
+  });
+}
+
+int hfr_model_wait_host(hfr_model* m, int slot) {
+  return guarded([&] {
+    if (!m) throw Error(HFR_ERR_INVALID, "null model");
+    if (slot < 0 || slot >= hfr_model::kHostSlots) throw Error(HFR_ERR_INVALID, "slot out of range");
+    hfr_model::HostSlot& h = m->slots[slot];
+    if (!h.busy) return;
+    cuda_check(cudaEventSynchronize(h.out_done), "cudaEventSynchronize");
+    h.busy = false;
   });
 }
 

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant
 // template parameter: every shared-memory offset is an immediate.
 struct DwPipeParams {
   int C, Ho, Wo, pad_t, pad_l, tiles_w, tiles_h, cblocks, act, round_tf32, stages, stage_bytes;
-  long long num_tiles;
+  int num_sp;  // spatial tiles: batch x tiles_h x tiles_w (each exists once per channel block)
 };
 
 template <typename T, int STRIDE, int VL>
@@ -378,10 +378,12 @@ __global__ void __launch_bounds__(16 * VL + 32) dwconv3x3_pipe_kernel(const __gr
   pdl_wait();       // loads of, and stores over, tensors of the predecessor only after it has completed
   __syncthreads();
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  auto decode = [&](long long t, int& b, int& oy0, int& ox0) {
-    const long long sp = t / p.cblocks;  // t % cblocks == cb by construction
-    b = (int)(sp / tiles_per_img);
-    const int r = (int)(sp - (long long)b * tiles_per_img);
+  // this CTA's tiles: channel block cb of spatial tiles sp0, sp0 + sp_step, ...  (32-bit arithmetic only: the loop
+  // runs in every thread, a 64-bit division costs as much as a third of a tile's FMAs)
+  const int sp0 = (int)(blockIdx.x / (unsigned)p.cblocks), sp_step = (int)(gridDim.x / (unsigned)p.cblocks);
+  auto decode = [&](int sp, int& b, int& oy0, int& ox0) {
+    b = sp / tiles_per_img;
+    const int r = sp - b * tiles_per_img;
     const int ty = r / p.tiles_w;
     oy0 = ty * 8;
     ox0 = (r - ty * p.tiles_w) * 8;
@@ -390,9 +392,9 @@ __global__ void __launch_bounds__(16 * VL + 32) dwconv3x3_pipe_kernel(const __gr
     // ------------------------------------------------------------ producer
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int sp = sp0; sp < p.num_sp; sp += sp_step) {
       int b, oy0, ox0;
-      decode(t, b, oy0, ox0);
+      decode(sp, b, oy0, ox0);
       mbar_wait(empty0 + 8u * stage, phase ^ 1);
       if (elect_one()) {
         mbar_expect_tx(full0 + 8u * stage, (uint32_t)(TWI * THI * CBE * sizeof(T)));
@@ -420,9 +422,9 @@ __global__ void __launch_bounds__(16 * VL + 32) dwconv3x3_pipe_kernel(const __gr
     const size_t row_pitch = (size_t)p.Wo * p.C;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int sp = sp0; sp < p.num_sp; sp += sp_step) {
       int b, oy0, ox0;
-      decode(t, b, oy0, ox0);
+      decode(sp, b, oy0, ox0);
       mbar_wait(full0 + 8u * stage, phase);
       const T* xin = reinterpret_cast<const T*>(ring + (size_t)stage * p.stage_bytes) + in_off;
       float acc[4][VN];

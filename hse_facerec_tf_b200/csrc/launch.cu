@@ -218,7 +218,10 @@ static void launch_dw_pipe_t(const DwArgs& a, int prec, int device, cudaStream_t
   p.stages = (52 * 1024) / p.stage_bytes;
   if (p.stages < 2) p.stages = 2;
   if (p.stages > 6) p.stages = 6;
-  p.num_tiles = (long long)a.B * p.tiles_w * p.tiles_h * p.cblocks;
+  const long long num_sp = (long long)a.B * p.tiles_w * p.tiles_h;
+  if (num_sp * p.cblocks >= (1ll << 31)) throw Error(-1, "depthwise: too many tiles for one launch");
+  p.num_sp = (int)num_sp;
+  const long long num_tiles = num_sp * p.cblocks;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
   auto kern = dwconv3x3_pipe_kernel<T, STRIDE, VL>;
   static std::atomic<int> ctas_per_sm[64];  // per instantiation; the stage count is a function of the instantiation only
@@ -230,7 +233,7 @@ static void launch_dw_pipe_t(const DwArgs& a, int prec, int device, cudaStream_t
     ctas_per_sm[device].store(occ);
   }
   long long grid = (long long)device_sm_count(device) * ctas_per_sm[device].load();
-  if (grid > p.num_tiles) grid = p.num_tiles;
+  if (grid > num_tiles) grid = num_tiles;
   grid = grid / p.cblocks * p.cblocks;      // every CTA keeps one channel block
   if (grid < p.cblocks) grid = p.cblocks;
   launch_pdl(kern, dim3((unsigned)grid), dim3(16 * VL + 32), smem, s, tm, a.w, a.bias, (T*)a.y, p);

@@ -90,6 +90,16 @@ class TensorFlowInference:
         return out
 
 
+    def extract_stream(self, batches, l2norm=False, depth=2):
+        """The dataset loop of facerec_test.py:394 with batches instead of single files: an iterable of host batches
+        ([B,H,W,3] uint8 RGB crops, or float32 already pre-processed) -> a generator of [B,D] float32 arrays, `depth`
+        batches in flight so that uploads and downloads overlap the compute.  Each yielded array is reused `depth`
+        batches later - copy it (np.vstack / .copy()) if it has to outlive that."""
+        for (out,) in self.model.stream_host(batches, depth=depth, convert2BGR=self.convert2BGR,
+                                             imageNetUtilsMean=self.imageNetUtilsMean, l2norm=l2norm, graph=True):
+            yield out
+
+
 def extract_keras_features(model, img_filepath, crop_center):
     """facerec_test.py:128-147 with `model` a TensorFlowInference built from the Keras .h5/.pb (caffe-mode
     preprocess_input == convert2BGR + ImageNet mean).  Keras' load_img resizes with PIL nearest by default."""

@@ -120,6 +120,60 @@ class HfrModel:
             check(lib.hfr_model_forward_host(self._h, x.ctypes.data, dt, B, flags, ptrs, _stream_ptr(self.device)))
         return outs
 
+    HOST_SLOTS = 4
+
+    def submit_host(self, slot, x: np.ndarray, outs, convert2BGR=True, imageNetUtilsMean=True, l2norm=False, graph=True):
+        """Asynchronous half of forward_host: enqueue upload + forward + download of one batch on `slot`; `outs` (float32
+        [B, out_dims[i]] arrays, ideally page-locked like `x`) are valid after wait_host(slot).  The arrays must stay
+        alive and untouched until then."""
+        if x.ndim != 4 or tuple(x.shape[1:]) != (self.h, self.w, self.c) or not x.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"expected a contiguous input [B,{self.h},{self.w},{self.c}], got {tuple(x.shape)}")
+        if x.dtype == np.uint8:
+            dt = _lib.IN_U8
+        elif x.dtype == np.float32:
+            dt = _lib.IN_F32
+        else:
+            raise ValueError("submit_host takes uint8 or float32 batches")
+        B = x.shape[0]
+        for o, d in zip(outs, self.out_dims):
+            if o.dtype != np.float32 or tuple(o.shape) != (B, d) or not o.flags["C_CONTIGUOUS"]:
+                raise ValueError("outs must be contiguous float32 arrays of shape [B, out_dim]")
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        flags = self._flags(convert2BGR, imageNetUtilsMean, l2norm, graph, dt == _lib.IN_U8)
+        with torch.cuda.device(self.device):
+            check(lib.hfr_model_submit_host(self._h, int(slot), x.ctypes.data, dt, B, flags, ptrs, _stream_ptr(self.device)))
+
+    def wait_host(self, slot):
+        check(lib.hfr_model_wait_host(self._h, int(slot)))
+
+    def stream_host(self, batches, depth=2, **kw):
+        """Generator over an iterable of host batches -> lists of page-locked float32 outputs, `depth` batches in flight
+        (upload of batch i+1 and download of batch i-1 overlap the compute of batch i).  Each yielded list is reused
+        `depth` batches later: copy what must outlive that."""
+        depth = max(1, min(int(depth), self.HOST_SLOTS))
+        pinned, pending, bufs = {}, [], {}
+        for i, x in enumerate(batches):
+            slot = i % depth
+            if len(pending) == depth:
+                s0 = pending.pop(0)
+                self.wait_host(s0)
+                yield bufs[s0]
+            x = np.ascontiguousarray(x)
+            if x.dtype != np.uint8:
+                x = x.astype(np.float32, copy=False)
+            key = (slot, x.shape, x.dtype.str)
+            if key not in pinned:   # page-locked staging copies of the input and the outputs, one set per slot
+                pinned[key] = (torch.empty(x.shape, dtype=torch.uint8 if x.dtype == np.uint8 else torch.float32).pin_memory(),
+                               [torch.empty((x.shape[0], d), dtype=torch.float32).pin_memory() for d in self.out_dims])
+            hx, ho = pinned[key]
+            hx.numpy()[...] = x
+            bufs[slot] = [o.numpy() for o in ho]
+            self.submit_host(slot, hx.numpy(), bufs[slot], **kw)
+            pending.append(slot)
+        for s0 in pending:
+            self.wait_host(s0)
+            yield bufs[s0]
+
     # ---- per-layer timing ----------------------------------------------------------------------
     def layer_timing(self, enable=True):
         check(lib.hfr_model_set_layer_timing(self._h, int(enable)))

@@ -83,6 +83,16 @@ int hfr_model_forward(hfr_model* m, const void* x, int in_dtype, int batch, int 
  * batch host->device, runs, copies the outputs device->host and synchronises the stream. */
 int hfr_model_forward_host(hfr_model* m, const void* x_host, int in_dtype, int batch, int flags, void* const* outs_host,
                            void* stream);
+/* The same call split in two for callers that stream many batches (the reference's loop over a dataset,
+ * facerec_test.py:394): submit returns as soon as the H2D copy, the forward and the D2H copy of the batch are enqueued -
+ * the copies on the handle's own copy streams, the forward on `stream` - so the next batch's upload and the previous
+ * batch's download overlap the current batch's compute.  Up to HFR_HOST_SLOTS batches may be in flight, one per slot;
+ * outs_host[i] are valid after hfr_model_wait_host(m, slot).  x_host / outs_host should be page-locked for the copies to
+ * be asynchronous.  Submitting to a slot that has not been waited for is an error. */
+#define HFR_HOST_SLOTS 4
+int hfr_model_submit_host(hfr_model* m, int slot, const void* x_host, int in_dtype, int batch, int flags,
+                          void* const* outs_host, void* stream);
+int hfr_model_wait_host(hfr_model* m, int slot);
 /* Debug: give every activation its own buffer (no arena reuse) so hfr_model_debug_layer can read any of them. */
 int hfr_model_set_keep_activations(hfr_model* m, int keep);
 /* Intermediate activation of layer `layer_index` (plan order) from the last forward, converted to float32 NHWC on the

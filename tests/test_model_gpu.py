@@ -195,3 +195,53 @@ def test_keras_h5_on_gpu_matches_pb_twin(tmp_path):
     assert torch.equal(a, b)
     (ref,) = GraphOracle(pb).run(["reshape_1/Reshape:0"], {"input_1:0": preprocess_rgb_u8(u8)})
     assert cosine(a.cpu().numpy(), ref.reshape(5, -1)).min() > 0.9999
+
+
+def test_host_buffer_calls_blocking_and_pipelined(age_gender_pb):
+    """numpy in / numpy out: the blocking call equals the device call, and the pipelined stream (upload of batch i+1
+    and download of batch i-1 overlapping the compute of batch i) equals the blocking call batch for batch - including
+    a ragged last batch, CUDA-graph replay on and off, and the slot protocol's errors."""
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", ["age_pred/Softmax:0", "global_pooling/Mean:0"], precision="bf16")
+    rs = np.random.RandomState(11)
+    batches = [rs.randint(0, 256, (b, 224, 224, 3)).astype(np.uint8) for b in (6, 6, 6, 6, 6, 3)]
+    dev = [[o.cpu().numpy() for o in m.forward(torch.from_numpy(x).cuda())] for x in batches]
+    for x, d in zip(batches[:2], dev[:2]):
+        for got, want in zip(m.forward_host(x), d):
+            np.testing.assert_array_equal(got, want)
+    for graph in (False, True):
+        for depth in (1, 2, 4):
+            outs = [[o.copy() for o in res] for res in m.stream_host(batches, depth=depth, graph=graph)]
+            assert len(outs) == len(batches)
+            for res, d in zip(outs, dev):
+                assert [o.shape for o in res] == [o.shape for o in d]
+                for got, want in zip(res, d):
+                    np.testing.assert_array_equal(got, want)
+    # float32 host batches take the same path
+    xf = batches[0].astype(np.float32)
+    (want,) = [m.forward(torch.from_numpy(xf).cuda())[1].cpu().numpy()]
+    np.testing.assert_array_equal(list(m.stream_host([xf]))[0][1], want)
+    # slot protocol
+    hx = torch.from_numpy(batches[0]).pin_memory().numpy()
+    ho = [np.empty((6, d), np.float32) for d in m.out_dims]
+    m.wait_host(0)                                    # idle slot: no-op
+    m.submit_host(0, hx, ho)
+    with pytest.raises(hfr.HfrError):
+        m.submit_host(0, hx, ho)                      # still in flight
+    m.wait_host(0)
+    np.testing.assert_array_equal(ho[1], dev[0][1])
+    with pytest.raises(ValueError):
+        m.submit_host(hfr.HfrModel.HOST_SLOTS, hx, ho)
+    with pytest.raises(ValueError):
+        m.submit_host(0, hx[:, :100], ho)
+    with pytest.raises(ValueError):
+        m.submit_host(0, hx, [o.astype(np.float64) for o in ho])
+
+
+def test_extract_stream_matches_extract_batch(age_gender_pb):
+    tfi = hfr.TensorFlowInference(age_gender_pb, "input_1:0", "global_pooling/Mean:0", precision="bf16", input_hw=192)
+    rs = np.random.RandomState(5)
+    batches = [rs.randint(0, 256, (b, 192, 192, 3)).astype(np.uint8) for b in (8, 8, 8, 5)]
+    want = np.vstack([tfi.extract_batch(x, l2norm=True) for x in batches])
+    got = np.vstack([o.copy() for o in tfi.extract_stream(iter(batches), l2norm=True)])
+    np.testing.assert_array_equal(got, want)
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)

@@ -11,17 +11,40 @@ UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e
 
 
 def kernel_class(name):
+    """class from the kernel name alone (fallback when the plan is not available)"""
     if "gemm_tc_kernel" in name:
         mode = name.split("<")[1].split(">")[0].replace(" ", "").split(",")
         epi, amode = mode[2], mode[3]
         if epi == "1":
             return "knn"
         return {"0": "pw", "1": "conv", "2": "stem"}[amode]
-    for key, cls in (("conv_window", "stem"), ("stem_s2d", "stem"), ("stem_conv", "stem"), ("dwconv3x3", "dw"), ("dwpw", "dwpw"),
+    if "conv_window_kernel<4" in name.replace(" ", ""):
+        return "stem"
+    for key, cls in (("conv_window", "conv"), ("stem_s2d", "stem"), ("stem_conv", "stem"), ("dwconv3x3", "dw"), ("dwpw", "dwpw"),
                      ("maxpool", "maxpool"), ("subsample", "subsample"), ("gap_kernel", "gap"), ("fc_kernel", "fc")):
         if key in name:
             return cls
     return "other"
+
+
+def plan_classes(workload):
+    """Class of every launch of one eager step, in launch order, from the compiled plan (host-only load): the same
+    layer kinds bench.py books times under.  A bf16 stem is two launches (space-to-depth + window conv); a subsample
+    whose consumers are all 1x1 layers is not launched (they fetch the strided pixels through an im2col map)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import hse_facerec_tf_b200 as hfr
+    spec = bench.model_spec(workload, "bf16")
+    m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
+    layers = m.plan()["layers"]
+    seq = []
+    for i, L in enumerate(layers):
+        if L["kind"] == "subsample":
+            users = [U for U in layers if U["in"] == L["out"] or U.get("in2", -1) == L["out"]]
+            if users and all(U["kind"] == "pw" and U["in"] == L["out"] for U in users):
+                continue
+        seq += ["stem", "stem"] if L["kind"] == "stem" else [L["kind"]]
+    return seq
 
 
 def main():
@@ -32,9 +55,18 @@ def main():
         d = by.setdefault(r["ID"], {"name": r["Kernel Name"]})
         d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
     launches = list(by.values())[:per_step]
+    try:
+        seq = plan_classes(workload)
+    except Exception as e:  # noqa: BLE001
+        print("plan not available, classifying by kernel name:", e, file=sys.stderr)
+        seq = None
+    if seq is not None and len(seq) != len(launches):
+        print(f"plan has {len(seq)} launches, list has {len(launches)}: classifying by kernel name", file=sys.stderr)
+        seq = None
     agg = {}
-    for d in launches:
-        c = agg.setdefault(kernel_class(d["name"]), dict(launches=0, us=0.0, dram_bytes=0.0, l2_bytes=0.0))
+    for i, d in enumerate(launches):
+        cls = seq[i] if seq else kernel_class(d["name"])
+        c = agg.setdefault(cls, dict(launches=0, us=0.0, dram_bytes=0.0, l2_bytes=0.0))
         c["launches"] += 1
         c["us"] += d.get("gpu__time_duration.sum", 0.0)
         c["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)

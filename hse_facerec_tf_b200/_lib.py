@@ -31,6 +31,7 @@ SIGNATURES = {
     "hfr_model_get_layer_times": (_i, [_vp, _vp, C.POINTER(_i)]),
     "hfr_model_free": (None, [_vp]),
     "hfr_crop_resize_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "hfr_resize_pil_u8": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "hfr_age_gender_post": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hfr_l2_normalize": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "hfr_knn_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),

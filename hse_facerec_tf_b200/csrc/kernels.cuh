@@ -177,6 +177,122 @@ __global__ void crop_resize_u8_kernel(const uint8_t* __restrict__ frames, int H,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// scipy.misc.imresize(img, size, interp='bilinear') (facerec_test.py:84,93) = Pillow's Image.resize(BILINEAR) on uint8:
+// separable triangle filter widened by the scale factor when shrinking, coefficients normalised in double and quantised
+// to 22-bit fixed point, horizontal pass first with its result rounded to uint8, then the vertical pass (Pillow
+// libImaging/Resample.c, restated in oracle/resize.py).  Bit-exact: the double arithmetic uses the explicit _rn
+// intrinsics so that no multiply-add is contracted differently from the host library.
+// One CTA per (image, output row): the input rows that row needs are resampled horizontally into shared memory as
+// uint8, then combined vertically.  desc[i] = {byte offset, height, width, row pitch}.
+constexpr int kPilPrecisionBits = 32 - 8 - 2;
+constexpr int kPilMaxTaps = 64;  // filter taps per output sample: 2 * ceil(max(scale, 1)) + 1  (scale <= 31)
+
+struct PilAxis {
+  double scale, support, ss;
+};
+__device__ __forceinline__ PilAxis pil_axis(int in_size, int out_size) {
+  PilAxis a;
+  a.scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double fs = a.scale < 1.0 ? 1.0 : a.scale;
+  a.support = fs;  // bilinear support 1.0 * filterscale
+  a.ss = __ddiv_rn(1.0, fs);
+  return a;
+}
+// window [x0, x0 + n) and fixed-point coefficients of output sample xx
+__device__ __forceinline__ void pil_coeffs(const PilAxis& a, int in_size, int xx, int& x0, int& n, int* k) {
+  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), a.scale);
+  x0 = (int)__dadd_rn(__dadd_rn(center, -a.support), 0.5);
+  if (x0 < 0) x0 = 0;
+  int x1 = (int)__dadd_rn(__dadd_rn(center, a.support), 0.5);
+  if (x1 > in_size) x1 = in_size;
+  n = x1 - x0;
+  double ww = 0.0;
+  for (int x = 0; x < n; ++x) {
+    double t = __dmul_rn(__dadd_rn(__dadd_rn((double)(x + x0), -center), 0.5), a.ss);
+    if (t < 0.0) t = -t;
+    const double w = t < 1.0 ? __dadd_rn(1.0, -t) : 0.0;
+    ww = __dadd_rn(ww, w);
+  }
+  for (int x = 0; x < n; ++x) {
+    double t = __dmul_rn(__dadd_rn(__dadd_rn((double)(x + x0), -center), 0.5), a.ss);
+    if (t < 0.0) t = -t;
+    double w = t < 1.0 ? __dadd_rn(1.0, -t) : 0.0;
+    if (ww != 0.0) w = __ddiv_rn(w, ww);
+    const double q = __dmul_rn(w, (double)(1 << kPilPrecisionBits));
+    k[x] = w < 0.0 ? (int)__dadd_rn(-0.5, q) : (int)__dadd_rn(0.5, q);
+  }
+}
+__device__ __forceinline__ int pil_clip8(int acc) {
+  const int v = acc >> kPilPrecisionBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256) resize_pil_bilinear_u8_kernel(const uint8_t* __restrict__ images,
+                                                                     const long long* __restrict__ desc,
+                                                                     uint8_t* __restrict__ out, int oh, int ow) {
+  extern __shared__ uint8_t pil_rows[];  // [taps_v][ow][3] horizontally resampled rows
+  __shared__ int kv[kPilMaxTaps];
+  __shared__ int y0_s, ny_s;
+  const int img = blockIdx.y, oy = blockIdx.x;
+  const long long off = desc[img * 4 + 0];
+  const int H = (int)desc[img * 4 + 1], W = (int)desc[img * 4 + 2];
+  const long long pitch = desc[img * 4 + 3];
+  const uint8_t* src = images + off;
+  if (threadIdx.x == 0) {
+    int y0, ny;
+    if (H == oh) {  // Pillow skips the vertical pass entirely
+      y0 = oy;
+      ny = 1;
+      kv[0] = 1 << kPilPrecisionBits;
+    } else {
+      pil_coeffs(pil_axis(H, oh), H, oy, y0, ny, kv);
+    }
+    y0_s = y0;
+    ny_s = ny;
+  }
+  __syncthreads();
+  const int y0 = y0_s, ny = ny_s;
+  const PilAxis ax = pil_axis(W, ow);
+  for (int ox = threadIdx.x; ox < ow; ox += blockDim.x) {
+    int kh[kPilMaxTaps];
+    int x0, nx;
+    if (W == ow) {  // no horizontal pass
+      x0 = ox;
+      nx = 1;
+      kh[0] = 1 << kPilPrecisionBits;
+    } else {
+      pil_coeffs(ax, W, ox, x0, nx, kh);
+    }
+    for (int j = 0; j < ny; ++j) {
+      const uint8_t* row = src + (long long)(y0 + j) * pitch + (long long)x0 * 3;
+      int a0 = 1 << (kPilPrecisionBits - 1), a1 = a0, a2 = a0;
+      for (int x = 0; x < nx; ++x) {
+        a0 += (int)row[3 * x] * kh[x];
+        a1 += (int)row[3 * x + 1] * kh[x];
+        a2 += (int)row[3 * x + 2] * kh[x];
+      }
+      uint8_t* d = pil_rows + ((size_t)j * ow + ox) * 3;
+      if (W == ow) {  // the pass is skipped, not applied with a unit coefficient (identical, but keep the bytes as they are)
+        d[0] = row[0]; d[1] = row[1]; d[2] = row[2];
+      } else {
+        d[0] = (uint8_t)pil_clip8(a0); d[1] = (uint8_t)pil_clip8(a1); d[2] = (uint8_t)pil_clip8(a2);
+      }
+    }
+  }
+  __syncthreads();
+  uint8_t* orow = out + (((size_t)img * oh + oy) * ow) * 3;
+  for (int i = threadIdx.x; i < ow * 3; i += blockDim.x) {
+    if (H == oh) {
+      orow[i] = pil_rows[i];
+    } else {
+      int acc = 1 << (kPilPrecisionBits - 1);
+      for (int j = 0; j < ny; ++j) acc += (int)pil_rows[(size_t)j * ow * 3 + i] * kv[j];
+      orow[i] = (uint8_t)pil_clip8(acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Stem on the tensor cores, step 1: space-to-depth staging of the uint8 image for a stride-2 KHxKW convolution.
 //   S[b, Y, X, (dy*2+dx)*3 + j] = u8[b, 2Y+dy-pt, 2X+dx-pl, j]   (0 outside the image)      j = raw channel 0..2
 //   S[b, Y, X, 12..15]          = 1 inside the image, 0 in the padding ("valid" channels: they carry the folded

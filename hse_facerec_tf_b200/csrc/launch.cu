@@ -678,6 +678,23 @@ void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, i
   HFR_LAUNCH_CHECK("crop_resize_u8");
 }
 
+void launch_resize_pil(const uint8_t* images, const long long* desc, int n, uint8_t* out, int oh, int ow, int taps_v,
+                       cudaStream_t s) {
+  if (n <= 0) return;
+  if (taps_v > kPilMaxTaps) throw Error(-5, "PIL resize: more than 31x reduction is not supported");
+  const size_t smem = (size_t)taps_v * ow * 3;
+  if (smem > 200 * 1024) throw Error(-5, "PIL resize: output row cache exceeds shared memory");
+  if (n > 65535) throw Error(-1, "PIL resize: at most 65535 images per call");
+  static std::atomic<bool> configured{false};
+  if (smem > 48 * 1024 && !configured.load()) {
+    cuda_check(cudaFuncSetAttribute(resize_pil_bilinear_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+               "cudaFuncSetAttribute(pil resize smem)");
+    configured.store(true);
+  }
+  resize_pil_bilinear_u8_kernel<<<dim3((unsigned)oh, (unsigned)n), 256, smem, s>>>(images, desc, out, oh, ow);
+  HFR_LAUNCH_CHECK("resize_pil_bilinear_u8");
+}
+
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {
   age_post_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(probs, age, B, N);
   HFR_LAUNCH_CHECK("age_post");

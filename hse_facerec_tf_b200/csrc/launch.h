@@ -119,6 +119,10 @@ void launch_fc(const float* x, const float* w, const float* bias, float* y, int 
 // crop + cv2-exact bilinear resize of uint8 RGB boxes: boxes [n][5] = (frame, x1, y1, x2, y2), device int32
 void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
                         cudaStream_t s);
+// Pillow-exact bilinear resize of n uint8 RGB images of arbitrary size (desc: device int64 [n][4] = byte offset, height,
+// width, row pitch); taps_v = the largest vertical tap count over the images (sizes the shared-memory row cache)
+void launch_resize_pil(const uint8_t* images, const long long* desc, int n, uint8_t* out, int oh, int ow, int taps_v,
+                       cudaStream_t s);
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s);
 void launch_l2norm(const float* x, float* y, int64_t n, int d, cudaStream_t s);
 void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream_t s);

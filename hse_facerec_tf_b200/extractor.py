@@ -90,6 +90,17 @@ class TensorFlowInference:
         return out
 
 
+    def extract_files(self, img_filepaths, crop_center=False, l2norm=False, batch=64):
+        """[self.extract_features(f, crop_center) for f in img_filepaths] (facerec_test.py:394) in batches: files are
+        decoded on the host, resized (Pillow-exact) and embedded on the GPU.  Returns float32 [n, D]."""
+        from .staging import load_resized_batch
+        outs = []
+        for i in range(0, len(img_filepaths), batch):
+            x = load_resized_batch(img_filepaths[i:i + batch], (self.h, self.w), crop_center, self.model.device)
+            outs.append(self.extract_batch(x, l2norm=l2norm, graph=False).cpu().numpy())
+        d = self.model.out_dims[0]
+        return np.concatenate(outs) if outs else np.empty((0, d), np.float32)
+
     def extract_stream(self, batches, l2norm=False, depth=2):
         """The dataset loop of facerec_test.py:394 with batches instead of single files: an iterable of host batches
         ([B,H,W,3] uint8 RGB crops, or float32 already pre-processed) -> a generator of [B,D] float32 arrays, `depth`

@@ -110,6 +110,14 @@ void hfr_model_free(hfr_model* m);
  * [n][5] = (frame index, x1, y1, x2, y2), already clamped to the frame with x2 > x1, y2 > y1.  out: [n,out_h,out_w,3]. */
 int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n,
                        uint8_t* out, int out_h, int out_w, int device, void* stream);
+/* Input staging, the other resize the reference uses: scipy.misc.imresize(img, (w, h), interp='bilinear')
+ * (facerec_test.py:84,93) = Pillow's Image.resize(BILINEAR) on the uint8 array (antialiasing triangle filter, 22-bit
+ * fixed-point coefficients, horizontal pass rounded to uint8 before the vertical one) - bit-exact.  `images`: device
+ * buffer holding n RGB uint8 images of arbitrary sizes; desc_host: HOST int64 [n][4] = (byte offset of pixel (0,0),
+ * height, width, row pitch in bytes) - a crop is an offset plus the parent's pitch.  out: device [n,out_h,out_w,3].
+ * Reductions beyond 31x are HFR_ERR_UNSUPPORTED. */
+int hfr_resize_pil_u8(const uint8_t* images, const int64_t* desc_host, int n, uint8_t* out, int out_h, int out_w,
+                      int device, void* stream);
 /* age = 1 + sum_{i in top2} i * p_i / sum_{top2} p   (facial_analysis.py:113-124); age_probs [batch, n] float32. */
 int hfr_age_gender_post(const float* age_probs, int batch, int n, float* age_out, int device, void* stream);
 /* sklearn.preprocessing.normalize(X, norm='l2') (facerec_test.py:262,265,405); in-place allowed (y == x). */

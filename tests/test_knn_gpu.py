@@ -32,7 +32,11 @@ def sk_margins(g, q):
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 @pytest.mark.parametrize("n,nq,d,normalised", [(5000, 300, 1024, True), (20000, 1000, 2048, True),
-                                               (3000, 257, 128, False), (70000, 700, 1024, False), (1, 5, 64, True)])
+                                               (3000, 257, 128, False), (70000, 700, 1024, False), (1, 5, 64, True),
+                                               # CTA-pair tiles with an odd number of 128-query blocks (the last pair's
+                                               # second CTA is entirely out of range); PCA-sized rows (D = 16, 128)
+                                               (40000, 1100, 1024, True), (30000, 130, 16, False), (2000, 50, 16, True),
+                                               (50000, 900, 128, False)])
 def test_kneighbors_matches_sklearn(precision, n, nq, d, normalised):
     g, q, pick = make_problem(n, nq, d, seed=n % 97, normalised=normalised)
     y = np.arange(n) % 1000

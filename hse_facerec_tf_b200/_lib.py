@@ -37,6 +37,7 @@ SIGNATURES = {
     "hfr_knn_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
     "hfr_knn_set_gallery": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "hfr_knn_query": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "hfr_knn_query_k": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "hfr_knn_query_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "hfr_knn_merge": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _vp]),
     "hfr_knn_free": (None, [_vp]),

@@ -1,4 +1,5 @@
-"""Drop-in for the reference's classifier: KNeighborsClassifier(n_neighbors=1, p=2) (facerec_test.py:272,422), used
+"""Drop-in for the reference's classifier: KNeighborsClassifier(n_neighbors=1, p=2) (facerec_test.py:272,422) - and the
+n_neighbors=3 entries of the same list (facerec_test.py:274-275; uniform weights, 1 <= n_neighbors <= 4 here) - used
 through the sklearn estimator protocol by classifier_tester / cross_validate (facerec_test.py:200-207) and by direct
 fit/predict (facerec_test.py:282-287,434-442); also valid as the last step of a Pipeline (facerec_test.py:271,421).
 
@@ -20,6 +21,8 @@ from .model import _stream_ptr
 
 
 class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
+    MAX_NEIGHBORS = 4
+
     def __init__(self, n_neighbors=1, p=2, *, device="cuda:0", precision="bf16", process_group=None, sharded=False):
         self.n_neighbors = n_neighbors
         self.p = p
@@ -55,8 +58,9 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
     def fit(self, X, y):
         """X: (N, D) gallery embeddings.  With sharded=True each rank passes ITS rows of the gallery (contiguous
         blocks in rank order) and the labels of the whole gallery are all-gathered."""
-        if self.n_neighbors != 1 or self.p != 2:
-            raise ValueError("only n_neighbors=1, p=2 (the reference's 1-NN) runs on the GPU path")
+        if self.p != 2 or not isinstance(self.n_neighbors, (int, np.integer)) or not 1 <= self.n_neighbors <= self.MAX_NEIGHBORS:
+            raise ValueError(f"the GPU path covers p=2 and 1 <= n_neighbors <= {self.MAX_NEIGHBORS} "
+                             "(the reference uses n_neighbors=1 and 3)")
         if not torch.cuda.is_available():
             raise _lib.HfrError("no CUDA device available; this classifier has no CPU fallback")
         self._free()
@@ -88,8 +92,12 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         if getattr(self, "_knn", None) is None:
             from sklearn.exceptions import NotFittedError
             raise NotFittedError("This KNeighborsClassifier instance is not fitted yet.")
-        if n_neighbors not in (None, 1):
-            raise ValueError("only the nearest neighbour is computed")
+        k = self.n_neighbors if n_neighbors is None else n_neighbors
+        if not isinstance(k, (int, np.integer)) or not 1 <= k <= self.MAX_NEIGHBORS:
+            raise ValueError(f"n_neighbors must be an integer in 1..{self.MAX_NEIGHBORS}, got {k!r}")
+        if k > len(self._labels):
+            raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {k}, n_samples_fit = "
+                             f"{len(self._labels)}, n_samples = {len(X)}")
         q = self._to_dev(X)
         if q.shape[1] != self.n_features_in_:
             raise ValueError(f"X has {q.shape[1]} features, but KNeighborsClassifier is expecting "
@@ -98,24 +106,40 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
             q = torch.nn.functional.pad(q, (0, self._pad))
         nq = q.shape[0]
         if nq == 0:
-            empty = np.zeros((0, 1), np.int64)
-            return (np.zeros((0, 1), np.float64), empty) if return_distance else empty
-        d2 = torch.empty(nq, dtype=torch.float32, device=q.device)
-        idx = torch.empty(nq, dtype=torch.int64, device=q.device)
+            empty = np.zeros((0, k), np.int64)
+            return (np.zeros((0, k), np.float64), empty) if return_distance else empty
         dev = q.device.index or 0
         stream = _stream_ptr(q.device)
-        check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, d2.data_ptr(), idx.data_ptr(), stream))
-        if self.sharded:
-            from .parallel import gather_pairs
-            d_all, i_all = gather_pairs(d2, idx, self.process_group)
-            check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), d_all.shape[0], nq, d2.data_ptr(), idx.data_ptr(),
-                                    dev, stream))
+        if k == 1:
+            d2 = torch.empty(nq, dtype=torch.float32, device=q.device)
+            idx = torch.empty(nq, dtype=torch.int64, device=q.device)
+            check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, d2.data_ptr(), idx.data_ptr(), stream))
+            if self.sharded:
+                from .parallel import gather_pairs
+                d_all, i_all = gather_pairs(d2, idx, self.process_group)
+                check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), d_all.shape[0], nq, d2.data_ptr(),
+                                        idx.data_ptr(), dev, stream))
+        else:
+            d2 = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            check(lib.hfr_knn_query_k(self._knn, q.data_ptr(), nq, int(k), d2.data_ptr(), idx.data_ptr(), stream))
+            if self.sharded:
+                from .parallel import gather_pairs, merge_topk
+                d_all, i_all = gather_pairs(d2, idx, self.process_group)      # [P, nq, k]
+                d2, idx = merge_topk(d_all, i_all, k)
         self._last_idx = idx
-        ind = idx.cpu().numpy().reshape(-1, 1)
+        ind = idx.cpu().numpy().reshape(nq, k)
         if return_distance:
-            return np.sqrt(np.maximum(d2.cpu().numpy().astype(np.float64), 0.0)).reshape(-1, 1), ind
+            return np.sqrt(np.maximum(d2.cpu().numpy().astype(np.float64), 0.0)).reshape(nq, k), ind
         return ind
 
     def predict(self, X):
-        ind = self.kneighbors(X, return_distance=False)[:, 0]
-        return self._labels[ind]
+        """Uniform-weight vote over the n_neighbors nearest rows; a tie goes to the smallest class (sklearn takes the
+        argmax of the class-probability row, classes_ being sorted).  n_neighbors=1 is a plain label lookup."""
+        ind = self.kneighbors(X, return_distance=False)
+        if ind.shape[1] == 1:
+            return self._labels[ind[:, 0]]
+        enc = self._y[ind]                                                   # class index of every neighbour, [nq, k]
+        votes = (enc[:, :, None] == enc[:, None, :]).sum(axis=2)             # votes[i, j] = #neighbours sharing j's class
+        key = votes.astype(np.int64) * (len(self.classes_) + 1) - enc        # more votes first, then the smaller class
+        return self.classes_[enc[np.arange(len(enc)), key.argmax(axis=1)]]

@@ -987,6 +987,40 @@ int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist
   });
 }
 
+int hfr_knn_query_k(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, float* dist2, int64_t* idx,
+                    void* stream) {
+  return guarded([&] {
+    if (!k || !queries || !dist2 || !idx || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (n_neighbors < 1 || n_neighbors > 4) throw Error(HFR_ERR_UNSUPPORTED, "k-NN on the GPU path supports 1 <= n_neighbors <= 4");
+    if (!k->gallery) throw Error(HFR_ERR_STATE, "hfr_knn_query_k before hfr_knn_set_gallery (NotFittedError)");
+    if (nq == 0) return;
+    use_device(k->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int splits, per;
+    knn_plan(nq, k->n_local, &splits, &per);
+    k->part_score.ensure((size_t)nq * splits * 8 * 4);  // [nq][splits][2 warpgroups][top-4]
+    k->part_idx.ensure((size_t)nq * splits * 8 * 4);
+    KnnGemmArgs a;
+    a.nq = nq; a.n = k->n_local; a.d = k->dim; a.splits = splits; a.n_blocks_per_unit = per;
+    a.cand = 4;
+    a.gnorm = (const float*)k->g_norm.p;
+    a.part_score = (float*)k->part_score.p;
+    a.part_idx = (int*)k->part_idx.p;
+    if (k->precision == HFR_BF16) {
+      k->q_lowp.ensure((size_t)nq * k->dim * 2);
+      launch_rows_prep(queries, k->q_lowp.p, nullptr, nq, k->dim, s);
+      a.q = k->q_lowp.p;
+      a.g = k->g_lowp.p;
+    } else {
+      a.q = queries;
+      a.g = k->gallery;
+    }
+    launch_knn_gemm(a, k->precision, k->device, s);
+    launch_knn_finalize_k(queries, k->gallery, a.part_score, a.part_idx, splits, nq, k->dim, k->row_offset, n_neighbors,
+                          dist2, idx, s);
+  });
+}
+
 int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host,
                        int64_t* best_idx_host, void* stream) {
   int rc = guarded([&] {

@@ -11,6 +11,7 @@
 //              Used by the 1x1 pointwise convolutions (A = NHWC activations viewed as [B*H*W, Cin]) and, with the
 //              im2col producer, by the 3x3 / 7x7 convolutions.
 //   EPI_KNN    score = gnorm[n] - 2*acc; running per-row top-2 over the unit's gallery range, written once per unit.
+//   EPI_KNN4   the same with a running top-4 (candidates for k-NN, k <= 4).
 //
 // Reference semantics being replaced: TF Conv2D(1x1)+Add+ReLU6 nodes `conv_pw_N*` of the frozen graph
 // (facerec_test.py:120 sess.run) and sklearn's ArgKmin euclidean reduction (facerec_test.py:272,284-285).
@@ -19,7 +20,7 @@
 
 namespace hfr {
 
-enum { EPI_STORE = 0, EPI_KNN = 1 };
+enum { EPI_STORE = 0, EPI_KNN = 1, EPI_KNN4 = 2 };  // EPI_KNN4: running top-4 per row (k-NN with k <= 4)
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2 };
 enum { AMODE_2D = 0, AMODE_IM2COL = 1, AMODE_STEM16 = 2 };
 
@@ -457,8 +458,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int u = unit0; u < p.num_units; u += unit_stride) {
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
+        constexpr int NC = (EPI == EPI_KNN4) ? 4 : 2;  // candidates kept per (row, gallery split, warpgroup)
         float b1 = INFINITY, b2 = INFINITY;
         int i1 = -1, i2 = -1;
+        [[maybe_unused]] float b3 = INFINITY, b4 = INFINITY;
+        [[maybe_unused]] int i3 = -1, i4 = -1;
         for (int nb = nb0; nb < nb0 + nbn; ++nb, ++tile) {
           if ((tile & 1) != (uint32_t)g) continue;
           const uint32_t aphase = my_tiles & 1;
@@ -481,7 +485,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float s = fmaf(-2.f, __uint_as_float(r[j]), gn[c * 32 + j]);
-              if (s < b2) {
+              if constexpr (NC == 4) {
+                if (s < b4) {  // sorted insert, strict '<': on equal scores the row seen first (lower index) stays ahead
+                  if (s < b2) {
+                    b4 = b3; i4 = i3;
+                    b3 = b2; i3 = i2;
+                    if (s < b1) {
+                      b2 = b1; i2 = i1;
+                      b1 = s; i1 = nbase + j;
+                    } else {
+                      b2 = s; i2 = nbase + j;
+                    }
+                  } else if (s < b3) {
+                    b4 = b3; i4 = i3;
+                    b3 = s; i3 = nbase + j;
+                  } else {
+                    b4 = s; i4 = nbase + j;
+                  }
+                }
+              } else if (s < b2) {
                 if (s < b1) {
                   b2 = b1;
                   i2 = i1;
@@ -505,11 +527,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (m < p.M) {
           // one (top-2) record per (row, gallery split, warpgroup)
           const int sp = nb0 / p.n_blocks_per_unit;
-          const size_t o = (((size_t)m * p.splits + sp) * 2 + g) * 2;
+          const size_t o = (((size_t)m * p.splits + sp) * 2 + g) * NC;
           p.part_score[o] = b1;
           p.part_score[o + 1] = b2;
           p.part_idx[o] = i1;
           p.part_idx[o + 1] = i2;
+          if constexpr (NC == 4) {
+            p.part_score[o + 2] = b3;
+            p.part_score[o + 3] = b4;
+            p.part_idx[o + 2] = i3;
+            p.part_idx[o + 3] = i4;
+          }
         }
       }
     }

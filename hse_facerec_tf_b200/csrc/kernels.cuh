@@ -1043,6 +1043,94 @@ __global__ void knn_finalize_kernel(const float* __restrict__ q, const float* __
   }
 }
 
+// k-NN variant (k <= 4): ncand = splits * 2 warpgroups * 4 candidates per query; the KEEP best approximate scores are
+// re-ranked exactly (fp64, as above) and the k nearest written in ascending (distance, index) order - the order
+// sklearn's kneighbors returns; missing neighbours (gallery smaller than k) are (inf, -1).
+template <int KEEP>
+__global__ void knn_finalize_k_kernel(const float* __restrict__ q, const float* __restrict__ g,
+                                      const float* __restrict__ part_score, const int* __restrict__ part_idx, int ncand,
+                                      long long nq, int d, long long row_offset, int k, float* __restrict__ out_dist,
+                                      long long* __restrict__ out_idx) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  float ls[KEEP];
+  int li[KEEP];
+#pragma unroll
+  for (int t = 0; t < KEEP; ++t) {
+    ls[t] = INFINITY;
+    li[t] = -1;
+  }
+  for (int j = lane; j < ncand; j += 32) {
+    float s = part_score[row * ncand + j];
+    int i = part_idx[row * ncand + j];
+    if (i < 0) continue;
+#pragma unroll
+    for (int t = 0; t < KEEP; ++t) {
+      if (s < ls[t] || (s == ls[t] && i < li[t])) {
+        const float ts = ls[t];
+        const int ti = li[t];
+        ls[t] = s;
+        li[t] = i;
+        s = ts;
+        i = ti;
+      }
+    }
+  }
+  double bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  int bi[4] = {-1, -1, -1, -1};
+  for (int c = 0; c < KEEP; ++c) {
+    float hs = ls[0];
+    int hi = li[0];
+    for (int o = 16; o; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, hs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, hi, o);
+      if (oi >= 0 && (hi < 0 || os < hs || (os == hs && oi < hi))) {
+        hs = os;
+        hi = oi;
+      }
+    }
+    if (hi < 0) break;
+    if (li[0] == hi) {
+#pragma unroll
+      for (int t = 0; t + 1 < KEEP; ++t) {
+        ls[t] = ls[t + 1];
+        li[t] = li[t + 1];
+      }
+      ls[KEEP - 1] = INFINITY;
+      li[KEEP - 1] = -1;
+    }
+    const float* qr = q + row * d;
+    const float* gr = g + (long long)hi * d;
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) {
+      const double df = (double)qr[j] - (double)gr[j];
+      acc = fma(df, df, acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // sorted insert into the exact top-4 (ascending distance, ties to the lowest index)
+    double cd = acc;
+    int ci = hi;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (ci >= 0 && (bi[t] < 0 || cd < bd[t] || (cd == bd[t] && ci < bi[t]))) {
+        const double td = bd[t];
+        const int ti = bi[t];
+        bd[t] = cd;
+        bi[t] = ci;
+        cd = td;
+        ci = ti;
+      }
+    }
+  }
+  if (lane == 0) {
+    for (int t = 0; t < k; ++t) {
+      out_dist[row * k + t] = (float)bd[t];
+      out_idx[row * k + t] = bi[t] < 0 ? -1 : row_offset + bi[t];
+    }
+  }
+}
+
 // Merge P per-shard results (gathered as [P][nq]) into the global best: smallest distance, ties to the lowest index.
 __global__ void knn_merge_kernel(const float* __restrict__ dist_all, const long long* __restrict__ idx_all, int parts,
                                  long long nq, float* __restrict__ best_dist, long long* __restrict__ best_idx) {

@@ -762,17 +762,33 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
   // and L2 bytes per flop; used when there is at least one wave of pair units
   static const char* pair_mode = getenv("HFR_PAIR");
   const int64_t pairs = (a.nq + 255) / 256;
-  if (!(pair_mode && pair_mode[0] == '0') && pairs * a.splits >= device_sm_count(device) / 2) {
+  const bool pair = !(pair_mode && pair_mode[0] == '0') && pairs * a.splits >= device_sm_count(device) / 2;
+  if (pair) {
     p.num_m_blocks = (int)pairs;
     p.num_units = p.num_m_blocks * a.splits;
-    CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 128);
-    if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);
-    else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);
-    return;
   }
-  CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, 256);
-  if (prec == PREC_BF16) launch_gemm_inst<__nv_bfloat16, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);
-  else launch_gemm_inst<float, 256, EPI_KNN, AMODE_2D>(tA, tB, tA, tA, p, device, s);
+  CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, pair ? 128 : 256);
+#define HFR_KNN_LAUNCH(T, EPI)                                                                       \
+  do {                                                                                               \
+    if (pair) launch_gemm_inst<T, 256, EPI, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);              \
+    else launch_gemm_inst<T, 256, EPI, AMODE_2D>(tA, tB, tA, tA, p, device, s);                      \
+  } while (0)
+  if (a.cand == 4) {
+    if (prec == PREC_BF16) HFR_KNN_LAUNCH(__nv_bfloat16, EPI_KNN4); else HFR_KNN_LAUNCH(float, EPI_KNN4);
+  } else {
+    if (prec == PREC_BF16) HFR_KNN_LAUNCH(__nv_bfloat16, EPI_KNN); else HFR_KNN_LAUNCH(float, EPI_KNN);
+  }
+#undef HFR_KNN_LAUNCH
+}
+
+void launch_knn_finalize_k(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
+                           int64_t nq, int d, int64_t row_offset, int k, float* out_dist, int64_t* out_idx,
+                           cudaStream_t s) {
+  if (nq <= 0) return;
+  if (k < 1 || k > 4) throw Error(-1, "k-NN: k must be 1..4");
+  knn_finalize_k_kernel<8><<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(q, g, part_score, part_idx, splits * 8, (long long)nq, d,
+                                                                    (long long)row_offset, k, out_dist, (long long*)out_idx);
+  HFR_LAUNCH_CHECK("knn_finalize_k");
 }
 
 void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,

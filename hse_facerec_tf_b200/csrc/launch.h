@@ -138,11 +138,16 @@ struct KnnGemmArgs {
   int* part_idx;
   int64_t nq, n;
   int d, splits, n_blocks_per_unit;
+  int cand = 2;  // candidates per (query, split, warpgroup): 2 (1-NN) or 4 (k-NN, k <= 4)
 };
 void knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
 void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s);
 void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
                          int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s);
+// k-NN (k <= 4) from 4-candidate partials: out_dist / out_idx are [nq][k], ascending
+void launch_knn_finalize_k(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
+                           int64_t nq, int d, int64_t row_offset, int k, float* out_dist, int64_t* out_idx,
+                           cudaStream_t s);
 void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
                       int64_t* best_idx, cudaStream_t s);
 

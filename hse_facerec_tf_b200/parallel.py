@@ -50,7 +50,8 @@ def shard_layout(n_local: int, y_local, group=None):
 
 
 def gather_pairs(d2: torch.Tensor, idx: torch.Tensor, group=None):
-    """All-gather per-rank (distance, global index) vectors -> ([P, nq] float32, [P, nq] int64) on d2's device."""
+    """All-gather per-rank (distance, global index) tensors ([nq] or [nq, k]) -> ([P, ...] float32, [P, ...] int64) on
+    d2's device."""
     rank, ws = world(group)
     if ws == 1:
         return d2.unsqueeze(0), idx.unsqueeze(0)
@@ -59,6 +60,19 @@ def gather_pairs(d2: torch.Tensor, idx: torch.Tensor, group=None):
     dist.all_gather(ds, d2.contiguous(), group=group)
     dist.all_gather(js, idx.contiguous(), group=group)
     return torch.stack(ds).contiguous(), torch.stack(js).contiguous()
+
+
+def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, k: int):
+    """Per-shard k-NN lists gathered as [P, nq, k] -> the global k nearest per query, ascending by (distance, index):
+    [nq, k] float32 / int64.  Shards that returned fewer than k rows pad with (inf, -1), which sort last."""
+    P, nq, kk = d_all.shape
+    d = d_all.permute(1, 0, 2).reshape(nq, P * kk)
+    i = i_all.permute(1, 0, 2).reshape(nq, P * kk)
+    big = torch.iinfo(torch.int64).max
+    order = torch.argsort(torch.where(i < 0, torch.full_like(i, big), i), dim=1, stable=True)   # ties -> lowest index
+    d, i = torch.gather(d, 1, order), torch.gather(i, 1, order)
+    order = torch.argsort(d, dim=1, stable=True)[:, :k]
+    return torch.gather(d, 1, order).contiguous(), torch.gather(i, 1, order).contiguous()
 
 
 def gather_rows(x: torch.Tensor, group=None):

@@ -132,6 +132,10 @@ int hfr_knn_create(int device, int dim, int precision /* HFR_TF32 or HFR_BF16 */
 int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64_t global_row_offset, void* stream);
 /* queries: device float32 [nq, dim] -> best_dist2 float32 [nq] (squared euclidean), best_idx int64 [nq] (global). */
 int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist2, int64_t* best_idx, void* stream);
+/* k nearest gallery rows, 1 <= n_neighbors <= 4 (the reference's classifier list also holds
+ * KNeighborsClassifier(n_neighbors=3, p=2), facerec_test.py:274-275): dist2 / idx are device [nq][n_neighbors], ascending
+ * by (exact squared distance, global index) like sklearn's kneighbors; (inf, -1) where the shard has fewer rows. */
+int hfr_knn_query_k(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, float* dist2, int64_t* idx, void* stream);
 /* Host-buffer variant of set_gallery+query for the end-to-end path (copies in, runs, copies out, synchronises). */
 int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host, int64_t* best_idx_host,
                        void* stream);

@@ -146,7 +146,8 @@ def test_empty_and_tiny_inputs():
     with pytest.raises(ValueError):
         hfr.KNeighborsClassifier().fit(np.zeros((0, 64), np.float32), np.zeros(0))
     with pytest.raises(ValueError):
-        hfr.KNeighborsClassifier(n_neighbors=3).fit(g, np.array([7, 8, 9]))
+        hfr.KNeighborsClassifier(n_neighbors=7).fit(g, np.array([7, 8, 9]))      # the GPU path stops at k = 4
+    assert hfr.KNeighborsClassifier(n_neighbors=3, precision="tf32").fit(g, np.array([7, 8, 9])).predict(g[:1])[0] == 7
 
 
 def test_extract_then_identify_end_to_end(age_gender_pb, golden_dir):
@@ -170,3 +171,40 @@ def test_extract_then_identify_end_to_end(age_gender_pb, golden_dir):
         pred = clf.predict(emb)                      # CUDA tensor in, labels out
         np.testing.assert_array_equal(pred, sk_pred)
         np.testing.assert_array_equal(pred, y[: len(imgs)])
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("k", [2, 3, 4])
+@pytest.mark.parametrize("n,nq,d", [(5000, 300, 1024), (40000, 700, 128), (3, 20, 64)])
+def test_k_nearest_neighbours_match_sklearn(precision, k, n, nq, d):
+    """KNeighborsClassifier(n_neighbors=3, p=2) of the reference's list (facerec_test.py:274-275): neighbour lists equal
+    sklearn's wherever consecutive exact distances differ by more than the stated tolerance, and the uniform vote -
+    ties to the smallest class - gives the same labels."""
+    if k > n:
+        pytest.skip("k > gallery size is an error, covered below")
+    g, q, _ = make_problem(n, nq, d, seed=7 + k, normalised=True)
+    y = (np.arange(n) * 7) % 23                                  # few classes: votes do collide
+    clf = hfr.KNeighborsClassifier(n_neighbors=k, p=2, precision=precision).fit(g, y)
+    sk = neighbors.KNeighborsClassifier(n_neighbors=k, p=2).fit(g, y)
+    sk_d, sk_i = sk.kneighbors(q)
+    dist, ind = clf.kneighbors(q)
+    assert dist.shape == ind.shape == (nq, k)
+    kk = min(k + 1, n)
+    dk = neighbors.NearestNeighbors(n_neighbors=kk, algorithm="brute").fit(g).kneighbors(q)[0] ** 2
+    clear = (np.diff(dk, axis=1) > 1e-6).all(axis=1)             # no (near-)ties among the first k+1 exact distances
+    assert clear.mean() > 0.95
+    np.testing.assert_array_equal(ind[clear], sk_i[clear])
+    np.testing.assert_allclose(dist[clear], sk_d[clear], rtol=1e-4, atol=2e-4)
+    np.testing.assert_array_equal(clf.predict(q)[clear], sk.predict(q)[clear])
+    # a per-call override, as sklearn allows
+    np.testing.assert_array_equal(clf.kneighbors(q, n_neighbors=1, return_distance=False)[clear][:, 0], sk_i[clear][:, 0])
+
+
+def test_k_neighbours_argument_errors():
+    g, q, _ = make_problem(50, 5, 64, seed=1)
+    with pytest.raises(ValueError):
+        hfr.KNeighborsClassifier(n_neighbors=5).fit(g, np.arange(50))      # beyond the GPU path's k <= 4
+    clf = hfr.KNeighborsClassifier(n_neighbors=3).fit(g[:2], np.arange(2))
+    with pytest.raises(ValueError):                                          # sklearn: n_neighbors <= n_samples_fit
+        clf.kneighbors(q)
+    np.testing.assert_array_equal(clf.kneighbors(q, n_neighbors=2, return_distance=False).shape, (5, 2))

@@ -189,6 +189,9 @@ CONV_CASES = [  # (B, H, W, cin, cout, k, stride)
     (2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1), (5, 7, 7, 512, 512, 3, 1),
     (1, 9, 11, 64, 128, 3, 1), (2, 16, 16, 64, 64, 3, 2),
     (128, 14, 14, 256, 256, 3, 1), (32, 28, 28, 128, 128, 3, 1), (40, 28, 28, 64, 256, 3, 2),  # CTA-pair tiles
+    # strided 1x1 convolutions (the gather the plan states as a subsample layer, fetched through the im2col map):
+    # pair tiles with K = 1024, plain tiles, odd spatial size
+    (64, 28, 28, 1024, 512, 1, 2), (2, 56, 56, 256, 128, 1, 2), (3, 27, 27, 128, 64, 1, 2),
 ]
 
 

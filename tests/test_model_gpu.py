@@ -171,6 +171,26 @@ def test_resnet50_synthetic_parity(precision, tmp_path):
         assert np.isfinite(g).all() and err <= tol * scale * (1 + li / 8), f"layer {li} {L['kind']} {L['name']}: {err} / {scale}"
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_resnet50_large_batch_takes_the_same_values_as_small_batches(precision, tmp_path):
+    """At the benchmark's batch size the launcher picks other tile shapes than at batch 3 (CTA-pair tiles for the 3x3
+    and long-K 1x1 layers, strided-im2col pairs, wider waves); every output element is still the same K-ordered sum, so
+    a large batch must reproduce the small-batch embeddings (which the test above pins against the oracle)."""
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    pb = write_resnet50_pb(str(tmp_path / "vgg2_resnet.pb"), seed=7)
+    B = 192
+    u8 = np.concatenate([smooth_images(8, 224, 3), np.random.RandomState(1).randint(0, 256, (B - 8, 224, 224, 3)).astype(np.uint8)])
+    m = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    x = torch.from_numpy(u8).cuda()
+    (big,) = m.forward(x, True, False)
+    (big_graph,) = m.forward(x, True, False, graph=True)
+    torch.testing.assert_close(big_graph, big, rtol=0, atol=0)
+    for lo, hi in ((0, 3), (5, 8), (B - 2, B)):
+        (small,) = m.forward(x[lo:hi].contiguous(), True, False)
+        scale = float(small.abs().max())
+        assert float((big[lo:hi] - small).abs().max()) <= 1e-5 * scale, (lo, hi)
+
+
 def test_forward_argument_errors(age_gender_pb):
     m = hfr.HfrModel(age_gender_pb, "input_1:0", ["global_pooling/Mean:0"], precision="bf16")
     x = torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device="cuda")

@@ -882,24 +882,32 @@ int hfr_resize_pil_u8(const uint8_t* images, const int64_t* desc_host, int n, ui
     if (n == 0) return;
     use_device(device);
     cudaStream_t s = (cudaStream_t)stream;
-    int taps_v = 1;
+    int taps_v = 1, taps_h = 1;
     for (int i = 0; i < n; ++i) {
       const int64_t h = desc_host[4 * i + 1], w = desc_host[4 * i + 2], pitch = desc_host[4 * i + 3];
       if (desc_host[4 * i] < 0 || h <= 0 || w <= 0 || pitch < 3 * w) throw Error(HFR_ERR_INVALID, "bad image descriptor");
       for (int axis = 0; axis < 2; ++axis) {
-        const double scale = (double)(axis ? w : h) / (axis ? out_w : out_h);
+        const int64_t in_size = axis ? w : h;
+        const int out_size = axis ? out_w : out_h;
+        if (in_size == out_size) continue;  // pass skipped: one identity tap
+        const double scale = (double)in_size / out_size;
         const int taps = (int)std::ceil(scale < 1.0 ? 1.0 : scale) * 2 + 1;
         if (taps > 64) throw Error(HFR_ERR_UNSUPPORTED, "PIL resize: more than 31x reduction is not supported");
-        if (axis == 0 && h != out_h && taps > taps_v) taps_v = taps;
+        int& t = axis ? taps_h : taps_v;
+        if (taps > t) t = taps;
       }
     }
     long long* d_desc = nullptr;
+    int* d_tab = nullptr;
     cuda_check(cudaMallocAsync((void**)&d_desc, (size_t)n * 4 * sizeof(long long), s), "cudaMallocAsync(desc)");
+    cuda_check(cudaMallocAsync((void**)&d_tab, resize_pil_table_ints(n, out_h, out_w, taps_h, taps_v) * sizeof(int), s),
+               "cudaMallocAsync(coefficient tables)");
     static_assert(sizeof(long long) == sizeof(int64_t), "descriptor width");
     // desc_host may be pageable: the copy is staged by the runtime before this call returns
     cuda_check(cudaMemcpyAsync(d_desc, desc_host, (size_t)n * 4 * sizeof(long long), cudaMemcpyHostToDevice, s),
                "cudaMemcpyAsync(desc)");
-    launch_resize_pil(images, d_desc, n, out, out_h, out_w, taps_v, s);
+    launch_resize_pil(images, d_desc, d_tab, n, out, out_h, out_w, taps_h, taps_v, s);
+    cuda_check(cudaFreeAsync(d_tab, s), "cudaFreeAsync(tables)");
     cuda_check(cudaFreeAsync(d_desc, s), "cudaFreeAsync(desc)");
   });
 }

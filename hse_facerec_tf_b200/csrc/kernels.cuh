@@ -227,68 +227,75 @@ __device__ __forceinline__ int pil_clip8(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+// Pass 1: coefficient tables, once per image and axis (the double-precision arithmetic lives only here).
+// tab layout per image: [ow] x (x0, count, k[taps_h])  then  [oh] x (y0, count, k[taps_v])   (ints)
+__global__ void pil_coeff_kernel(const long long* __restrict__ desc, int* __restrict__ tab, int oh, int ow, int taps_h,
+                                 int taps_v) {
+  const int img = blockIdx.y;
+  const int H = (int)desc[img * 4 + 1], W = (int)desc[img * 4 + 2];
+  const int per_img = ow * (2 + taps_h) + oh * (2 + taps_v);
+  int* t_h = tab + (size_t)img * per_img;
+  int* t_v = t_h + ow * (2 + taps_h);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ow + oh; i += gridDim.x * blockDim.x) {
+    const bool horiz = i < ow;
+    const int o = horiz ? i : i - ow;
+    const int in_size = horiz ? W : H, out_size = horiz ? ow : oh;
+    int* row = horiz ? t_h + (size_t)o * (2 + taps_h) : t_v + (size_t)o * (2 + taps_v);
+    int k[kPilMaxTaps];
+    int x0, n;
+    if (in_size == out_size) {  // Pillow skips the pass: identity
+      x0 = o;
+      n = 1;
+      k[0] = 1 << kPilPrecisionBits;
+    } else {
+      pil_coeffs(pil_axis(in_size, out_size), in_size, o, x0, n, k);
+    }
+    row[0] = x0;
+    row[1] = n;
+    for (int x = 0; x < n; ++x) row[2 + x] = k[x];
+  }
+}
+
+// Pass 2: one CTA per (image, output row): the input rows that row needs are resampled horizontally into shared memory
+// as uint8 (Pillow rounds between the passes), then combined vertically.
 __global__ void __launch_bounds__(256) resize_pil_bilinear_u8_kernel(const uint8_t* __restrict__ images,
                                                                      const long long* __restrict__ desc,
-                                                                     uint8_t* __restrict__ out, int oh, int ow) {
+                                                                     const int* __restrict__ tab,
+                                                                     uint8_t* __restrict__ out, int oh, int ow,
+                                                                     int taps_h, int taps_v) {
   extern __shared__ uint8_t pil_rows[];  // [taps_v][ow][3] horizontally resampled rows
-  __shared__ int kv[kPilMaxTaps];
-  __shared__ int y0_s, ny_s;
   const int img = blockIdx.y, oy = blockIdx.x;
   const long long off = desc[img * 4 + 0];
-  const int H = (int)desc[img * 4 + 1], W = (int)desc[img * 4 + 2];
   const long long pitch = desc[img * 4 + 3];
   const uint8_t* src = images + off;
-  if (threadIdx.x == 0) {
-    int y0, ny;
-    if (H == oh) {  // Pillow skips the vertical pass entirely
-      y0 = oy;
-      ny = 1;
-      kv[0] = 1 << kPilPrecisionBits;
-    } else {
-      pil_coeffs(pil_axis(H, oh), H, oy, y0, ny, kv);
-    }
-    y0_s = y0;
-    ny_s = ny;
-  }
-  __syncthreads();
-  const int y0 = y0_s, ny = ny_s;
-  const PilAxis ax = pil_axis(W, ow);
+  const int per_img = ow * (2 + taps_h) + oh * (2 + taps_v);
+  const int* t_h = tab + (size_t)img * per_img;
+  const int* t_v = t_h + ow * (2 + taps_h) + (size_t)oy * (2 + taps_v);
+  const int y0 = t_v[0], ny = t_v[1];
   for (int ox = threadIdx.x; ox < ow; ox += blockDim.x) {
-    int kh[kPilMaxTaps];
-    int x0, nx;
-    if (W == ow) {  // no horizontal pass
-      x0 = ox;
-      nx = 1;
-      kh[0] = 1 << kPilPrecisionBits;
-    } else {
-      pil_coeffs(ax, W, ox, x0, nx, kh);
-    }
+    const int* th = t_h + (size_t)ox * (2 + taps_h);
+    const int x0 = th[0], nx = th[1];
     for (int j = 0; j < ny; ++j) {
       const uint8_t* row = src + (long long)(y0 + j) * pitch + (long long)x0 * 3;
       int a0 = 1 << (kPilPrecisionBits - 1), a1 = a0, a2 = a0;
       for (int x = 0; x < nx; ++x) {
-        a0 += (int)row[3 * x] * kh[x];
-        a1 += (int)row[3 * x + 1] * kh[x];
-        a2 += (int)row[3 * x + 2] * kh[x];
+        const int kx = th[2 + x];
+        a0 += (int)row[3 * x] * kx;
+        a1 += (int)row[3 * x + 1] * kx;
+        a2 += (int)row[3 * x + 2] * kx;
       }
       uint8_t* d = pil_rows + ((size_t)j * ow + ox) * 3;
-      if (W == ow) {  // the pass is skipped, not applied with a unit coefficient (identical, but keep the bytes as they are)
-        d[0] = row[0]; d[1] = row[1]; d[2] = row[2];
-      } else {
-        d[0] = (uint8_t)pil_clip8(a0); d[1] = (uint8_t)pil_clip8(a1); d[2] = (uint8_t)pil_clip8(a2);
-      }
+      d[0] = (uint8_t)pil_clip8(a0);
+      d[1] = (uint8_t)pil_clip8(a1);
+      d[2] = (uint8_t)pil_clip8(a2);
     }
   }
   __syncthreads();
   uint8_t* orow = out + (((size_t)img * oh + oy) * ow) * 3;
   for (int i = threadIdx.x; i < ow * 3; i += blockDim.x) {
-    if (H == oh) {
-      orow[i] = pil_rows[i];
-    } else {
-      int acc = 1 << (kPilPrecisionBits - 1);
-      for (int j = 0; j < ny; ++j) acc += (int)pil_rows[(size_t)j * ow * 3 + i] * kv[j];
-      orow[i] = (uint8_t)pil_clip8(acc);
-    }
+    int acc = 1 << (kPilPrecisionBits - 1);
+    for (int j = 0; j < ny; ++j) acc += (int)pil_rows[(size_t)j * ow * 3 + i] * t_v[2 + j];
+    orow[i] = (uint8_t)pil_clip8(acc);
   }
 }
 

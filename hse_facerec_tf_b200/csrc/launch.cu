@@ -678,10 +678,13 @@ void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, i
   HFR_LAUNCH_CHECK("crop_resize_u8");
 }
 
-void launch_resize_pil(const uint8_t* images, const long long* desc, int n, uint8_t* out, int oh, int ow, int taps_v,
-                       cudaStream_t s) {
+size_t resize_pil_table_ints(int n, int oh, int ow, int taps_h, int taps_v) {
+  return (size_t)n * ((size_t)ow * (2 + taps_h) + (size_t)oh * (2 + taps_v));
+}
+void launch_resize_pil(const uint8_t* images, const long long* desc, int* tab, int n, uint8_t* out, int oh, int ow,
+                       int taps_h, int taps_v, cudaStream_t s) {
   if (n <= 0) return;
-  if (taps_v > kPilMaxTaps) throw Error(-5, "PIL resize: more than 31x reduction is not supported");
+  if (taps_v > kPilMaxTaps || taps_h > kPilMaxTaps) throw Error(-5, "PIL resize: more than 31x reduction is not supported");
   const size_t smem = (size_t)taps_v * ow * 3;
   if (smem > 200 * 1024) throw Error(-5, "PIL resize: output row cache exceeds shared memory");
   if (n > 65535) throw Error(-1, "PIL resize: at most 65535 images per call");
@@ -691,7 +694,10 @@ void launch_resize_pil(const uint8_t* images, const long long* desc, int n, uint
                "cudaFuncSetAttribute(pil resize smem)");
     configured.store(true);
   }
-  resize_pil_bilinear_u8_kernel<<<dim3((unsigned)oh, (unsigned)n), 256, smem, s>>>(images, desc, out, oh, ow);
+  pil_coeff_kernel<<<dim3((unsigned)((ow + oh + 127) / 128), (unsigned)n), 128, 0, s>>>(desc, tab, oh, ow, taps_h, taps_v);
+  HFR_LAUNCH_CHECK("pil_coeff");
+  resize_pil_bilinear_u8_kernel<<<dim3((unsigned)oh, (unsigned)n), 256, smem, s>>>(images, desc, tab, out, oh, ow, taps_h,
+                                                                                  taps_v);
   HFR_LAUNCH_CHECK("resize_pil_bilinear_u8");
 }
 

@@ -120,9 +120,11 @@ void launch_fc(const float* x, const float* w, const float* bias, float* y, int 
 void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
                         cudaStream_t s);
 // Pillow-exact bilinear resize of n uint8 RGB images of arbitrary size (desc: device int64 [n][4] = byte offset, height,
-// width, row pitch); taps_v = the largest vertical tap count over the images (sizes the shared-memory row cache)
-void launch_resize_pil(const uint8_t* images, const long long* desc, int n, uint8_t* out, int oh, int ow, int taps_v,
-                       cudaStream_t s);
+// width, row pitch); taps_h / taps_v = the largest tap counts over the images; tab: device scratch of
+// resize_pil_table_ints(n, oh, ow, taps_h, taps_v) ints for the coefficient tables
+size_t resize_pil_table_ints(int n, int oh, int ow, int taps_h, int taps_v);
+void launch_resize_pil(const uint8_t* images, const long long* desc, int* tab, int n, uint8_t* out, int oh, int ow,
+                       int taps_h, int taps_v, cudaStream_t s);
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s);
 void launch_l2norm(const float* x, float* y, int64_t n, int d, cudaStream_t s);
 void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream_t s);

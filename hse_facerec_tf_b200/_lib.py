@@ -32,6 +32,7 @@ SIGNATURES = {
     "hfr_model_free": (None, [_vp]),
     "hfr_crop_resize_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "hfr_resize_pil_u8": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "hfr_pairwise_dist": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
     "hfr_age_gender_post": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hfr_l2_normalize": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "hfr_knn_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),

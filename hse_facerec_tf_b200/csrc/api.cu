@@ -912,6 +912,24 @@ int hfr_resize_pil_u8(const uint8_t* images, const int64_t* desc_host, int n, ui
   });
 }
 
+int hfr_pairwise_dist(const float* x, int64_t n, const float* y, int64_t m, int dim, const float* year_x,
+                      const float* born_x, const float* year_y, const float* born_y, float age_weight, float* out,
+                      int device, void* stream) {
+  return guarded([&] {
+    if (!x || !out || n < 0 || m < 0 || dim <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!y) {
+      y = x;
+      if (m != n) throw Error(HFR_ERR_INVALID, "y == NULL means y = x: m must equal n");
+      year_y = year_x;
+      born_y = born_x;
+    }
+    const int given = (year_x != nullptr) + (born_x != nullptr) + (year_y != nullptr) + (born_y != nullptr);
+    if (given != 0 && given != 4) throw Error(HFR_ERR_INVALID, "the age penalty needs all of year/born for both sides");
+    use_device(device);
+    launch_pairwise_dist(x, y, n, m, dim, year_x, born_x, year_y, born_y, age_weight, out, (cudaStream_t)stream);
+  });
+}
+
 int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, void* stream) {
   return guarded([&] {
     if (!x || !y || n < 0 || dim <= 0) throw Error(HFR_ERR_INVALID, "bad argument");

@@ -1138,6 +1138,70 @@ __global__ void knn_finalize_k_kernel(const float* __restrict__ q, const float* 
   }
 }
 
+// Pairwise euclidean distance matrix for clustering (scope row 8f-3): out[i,j] = sqrt(sum_k (x[i,k] - y[j,k])^2), the
+// direct form the reference evaluates per pair (process_photos.py:46-48; facial_clustering_test.py:396-400 calls
+// sklearn's pairwise_distances, which upcasts to fp64 - the direct fp32 differences have no cancellation, so both agree
+// to fp32 rounding).  Optional album penalty (process_photos.py:49-52): + w * (a_i - a_j)^2 / (a_i + a_j) with
+// a = max(year_i, year_j) - born, the sum clipped at 0.  64x64 outputs per CTA, 4x4 per thread, K in 16-float slabs.
+__global__ void __launch_bounds__(256) pairwise_dist_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            long long n, long long m, int d,
+                                                            const float* __restrict__ year_x,
+                                                            const float* __restrict__ born_x,
+                                                            const float* __restrict__ year_y,
+                                                            const float* __restrict__ born_y, float age_w,
+                                                            int zero_diag, float* __restrict__ out) {
+  __shared__ float xs[16][64 + 1], ys[16][64 + 1];
+  const long long i0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread -> rows ty*4.., cols tx*4..
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, k = e & 15;
+      xs[k][r] = (i0 + r < n && k0 + k < d) ? x[(i0 + r) * d + k0 + k] : 0.f;
+      ys[k][r] = (j0 + r < m && k0 + k < d) ? y[(j0 + r) * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float xv[4], yv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xv[a] = xs[k][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) yv[b] = ys[k][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float df = xv[a] - yv[b];
+          acc[a][b] = fmaf(df, df, acc[a][b]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const long long i = i0 + ty * 4 + a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const long long j = j0 + tx * 4 + b;
+      if (j >= m) continue;
+      float v = sqrtf(acc[a][b]);
+      if (zero_diag && i == j) v = 0.f;
+      if (year_x != nullptr) {
+        const float my = fmaxf(year_x[i], year_y[j]);
+        const float ai = my - born_x[i], aj = my - born_y[j];
+        v = fmaxf(v + age_w * ((ai - aj) * (ai - aj) / (ai + aj)), 0.f);
+      }
+      out[i * m + j] = v;
+    }
+  }
+}
+
 // Merge P per-shard results (gathered as [P][nq]) into the global best: smallest distance, ties to the lowest index.
 __global__ void knn_merge_kernel(const float* __restrict__ dist_all, const long long* __restrict__ idx_all, int parts,
                                  long long nq, float* __restrict__ best_dist, long long* __restrict__ best_idx) {

@@ -701,6 +701,17 @@ void launch_resize_pil(const uint8_t* images, const long long* desc, int* tab, i
   HFR_LAUNCH_CHECK("resize_pil_bilinear_u8");
 }
 
+void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,
+                          const float* born_x, const float* year_y, const float* born_y, float age_w, float* out,
+                          cudaStream_t s) {
+  if (n <= 0 || m <= 0) return;
+  const int64_t gy = (n + 63) / 64, gx = (m + 63) / 64;
+  if (gy > 65535) throw Error(-1, "pairwise distances: too many rows for one launch");
+  pairwise_dist_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(x, y, (long long)n, (long long)m, d, year_x, born_x,
+                                                                         year_y, born_y, age_w, x == y ? 1 : 0, out);
+  HFR_LAUNCH_CHECK("pairwise_dist");
+}
+
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {
   age_post_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(probs, age, B, N);
   HFR_LAUNCH_CHECK("age_post");

@@ -150,6 +150,11 @@ void launch_knn_finalize(const float* q, const float* g, const float* part_score
 void launch_knn_finalize_k(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
                            int64_t nq, int d, int64_t row_offset, int k, float* out_dist, int64_t* out_idx,
                            cudaStream_t s);
+// pairwise euclidean distances (+ optional album age penalty), fp32 direct differences; y == x: the diagonal is forced
+// to exact zeros
+void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,
+                          const float* born_x, const float* year_y, const float* born_y, float age_w, float* out,
+                          cudaStream_t s);
 void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
                       int64_t* best_idx, cudaStream_t s);
 

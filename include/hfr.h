@@ -110,6 +110,14 @@ void hfr_model_free(hfr_model* m);
  * [n][5] = (frame index, x1, y1, x2, y2), already clamped to the frame with x2 > x1, y2 > y1.  out: [n,out_h,out_w,3]. */
 int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n,
                        uint8_t* out, int out_h, int out_w, int device, void* stream);
+/* Distance matrix for the clustering scripts: out[i,j] = ||x_i - y_j||_2 (float32 [n,m], device), the per-pair
+ * expression of process_photos.py:46-48 and sklearn.metrics.pairwise_distances(X_norm) of facial_clustering_test.py:396;
+ * y == NULL: y = x (m == n, exact zeros on the diagonal).  With year/born (device float32 [n] / [m], all four or none):
+ * out = max(0, dist + age_weight * (a_i - a_j)^2 / (a_i + a_j)), a = max(year_i, year_j) - born: the album variant of
+ * process_photos.py:49-56 (age_weight = 0.1 there).  Linkage itself stays on the host. */
+int hfr_pairwise_dist(const float* x, int64_t n, const float* y, int64_t m, int dim, const float* year_x,
+                      const float* born_x, const float* year_y, const float* born_y, float age_weight, float* out,
+                      int device, void* stream);
 /* Input staging, the other resize the reference uses: scipy.misc.imresize(img, (w, h), interp='bilinear')
  * (facerec_test.py:84,93) = Pillow's Image.resize(BILINEAR) on the uint8 array (antialiasing triangle filter, 22-bit
  * fixed-point coefficients, horizontal pass rounded to uint8 before the vertical one) - bit-exact.  `images`: device

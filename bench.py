@@ -282,8 +282,8 @@ def bench_network(args, rank, world, dev):
                               tflops=round(tf, 2), hbm_gbs=round(gb, 1))
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]
-    roof = dict(kernel={"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col)", "dw": "dwconv3x3_kernel",
-                        "stem": "stem_conv_kernel"}.get(dom, dom),
+    roof = dict(kernel={"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col) / conv_window_kernel", "dw": "dwconv3x3_pipe_kernel",
+                        "stem": "stem_s2d_kernel + conv_window_kernel" if args.precision == "bf16" else "stem_conv_kernel"}.get(dom, dom),
                 bound=kd["bound"], achieved=kd["achieved"], peak=pk["tensor"] if kd["bound"] == "tensor" else pk["hbm"],
                 unit=kd["unit"], frac=kd["frac"], traffic=None, peak_source=pk["source"] + " (sustained)",
                 per_launch_ms=round(kd["ms_per_step"] / kd["launches"], 5))

@@ -20,6 +20,15 @@ from ._lib import check, lib
 from .model import _stream_ptr
 
 
+def uniform_vote(enc: np.ndarray, n_classes: int) -> np.ndarray:
+    """enc: [nq, k] class indices (into the sorted classes_) of every query's neighbours -> [nq] winning class index under
+    uniform weights: most votes, a tie going to the smallest class index - sklearn's predict takes the argmax of the
+    class-probability row (neighbors/_classification.py), and argmax returns the first maximum."""
+    votes = (enc[:, :, None] == enc[:, None, :]).sum(axis=2)          # votes[i, j] = neighbours sharing neighbour j's class
+    key = votes.astype(np.int64) * (n_classes + 1) - enc              # more votes first, then the smaller class
+    return enc[np.arange(len(enc)), key.argmax(axis=1)]
+
+
 class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
     MAX_NEIGHBORS = 4
 
@@ -139,7 +148,4 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         ind = self.kneighbors(X, return_distance=False)
         if ind.shape[1] == 1:
             return self._labels[ind[:, 0]]
-        enc = self._y[ind]                                                   # class index of every neighbour, [nq, k]
-        votes = (enc[:, :, None] == enc[:, None, :]).sum(axis=2)             # votes[i, j] = #neighbours sharing j's class
-        key = votes.astype(np.int64) * (len(self.classes_) + 1) - enc        # more votes first, then the smaller class
-        return self.classes_[enc[np.arange(len(enc)), key.argmax(axis=1)]]
+        return self.classes_[uniform_vote(self._y[ind], len(self.classes_))]

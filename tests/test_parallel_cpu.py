@@ -111,3 +111,20 @@ def test_merge_topk_equals_global_knn_with_ties():
     clear[0] = False
     np.testing.assert_array_equal(idx.numpy()[clear], I[clear])
     np.testing.assert_allclose(np.sqrt(d2.numpy()[clear]), D[clear], rtol=1e-5)
+
+
+def test_uniform_vote_matches_sklearn_predict():
+    """The k-NN vote the classifier applies to the GPU's neighbour lists, fed here with sklearn's own lists: equal to
+    sklearn's predict for k = 2, 3, 4, including three-way ties (which go to the smallest class, not the nearest)."""
+    from hse_facerec_tf_b200.classifier import uniform_vote
+    rs = np.random.RandomState(5)
+    g = rs.randn(400, 6).astype(np.float32)
+    q = rs.randn(300, 6).astype(np.float32)
+    y = rs.randint(0, 9, 400) * 5 - 7                       # non-contiguous, negative labels
+    classes, enc_all = np.unique(y, return_inverse=True)
+    for k in (2, 3, 4):
+        sk = neighbors.KNeighborsClassifier(n_neighbors=k, p=2).fit(g, y)
+        ind = sk.kneighbors(q, return_distance=False)
+        pred = classes[uniform_vote(enc_all[ind], len(classes))]
+        np.testing.assert_array_equal(pred, sk.predict(q))
+        assert (np.array([len(set(r)) for r in enc_all[ind]]) == k).any()      # all-different rows did occur

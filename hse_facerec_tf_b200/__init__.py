@@ -13,6 +13,7 @@ from .age_gender import FacialImageProcessing  # noqa: F401
 from .classifier import KNeighborsClassifier  # noqa: F401
 from .preprocessing import normalize  # noqa: F401
 from . import parallel  # noqa: F401
+from .decomposition import PCA  # noqa: F401
 from .clustering import album_distance_matrix, pairwise_distances  # noqa: F401
 from .staging import crop_resize, expand_and_clamp_boxes, load_resized_batch, resize_pil  # noqa: F401
 

@@ -208,3 +208,35 @@ def test_k_neighbours_argument_errors():
     with pytest.raises(ValueError):                                          # sklearn: n_neighbors <= n_samples_fit
         clf.kneighbors(q)
     np.testing.assert_array_equal(clf.kneighbors(q, n_neighbors=2, return_distance=False).shape, (5, 2))
+
+
+@pytest.mark.parametrize("n_components,k", [(16, 1), (16, 3), (128, 1)])
+def test_pca_knn_pipeline_matches_sklearn(n_components, k):
+    """The reference's '1-NN+PCA' / '3-NN+PCA' entries (facerec_test.py:271-274, 417-422) with both steps on the GPU
+    against the same Pipeline in scikit-learn: the projection to fp32 rounding, the predictions wherever the exact
+    neighbour distances in the projected space are not (near-)tied."""
+    from sklearn.decomposition import PCA as SkPCA
+    from sklearn.pipeline import Pipeline
+    rs = np.random.RandomState(n_components + k)
+    n_ids, per_id, d = 120, 8, 1024
+    centres = preprocessing.normalize(rs.randn(n_ids, d))
+    X = preprocessing.normalize(np.repeat(centres, per_id, 0) + 0.35 * rs.randn(n_ids * per_id, d) / np.sqrt(d) * 8).astype(np.float32)
+    y = np.repeat(np.arange(n_ids), per_id)
+    test = rs.rand(len(X)) < 0.4
+    Xtr, ytr, Xte = X[~test], y[~test], X[test]
+    ours = Pipeline([("pca", hfr.PCA(n_components, svd_solver="full")), ("classifier", hfr.KNeighborsClassifier(n_neighbors=k, p=2, precision="tf32"))])
+    ref = Pipeline([("pca", SkPCA(n_components, svd_solver="full")), ("classifier", neighbors.KNeighborsClassifier(n_neighbors=k, p=2))])
+    ours.fit(Xtr, ytr)
+    ref.fit(Xtr, ytr)
+    Z, Zr = ours.named_steps["pca"].transform(Xte), ref.named_steps["pca"].transform(Xte)
+    assert Z.dtype == np.float32
+    np.testing.assert_allclose(Z, Zr, rtol=1e-4, atol=2e-5)
+    dk = neighbors.NearestNeighbors(n_neighbors=k + 1, algorithm="brute").fit(ref.named_steps["pca"].transform(Xtr)).kneighbors(Zr)[0] ** 2
+    clear = (np.diff(dk, axis=1) > 1e-5).all(axis=1)
+    assert clear.mean() > 0.9
+    np.testing.assert_array_equal(ours.predict(Xte)[clear], ref.predict(Xte)[clear])
+    assert abs(ours.score(Xte, y[test]) - ref.score(Xte, y[test])) < 0.02
+    # device-resident hand-over between the two steps
+    pca_t = hfr.PCA(n_components, svd_solver="full", output="torch").fit(Xtr)
+    zt = pca_t.transform(torch.from_numpy(Xte).cuda())
+    assert zt.is_cuda and np.array_equal(zt.cpu().numpy(), Z)

@@ -128,3 +128,29 @@ def test_uniform_vote_matches_sklearn_predict():
         pred = classes[uniform_vote(enc_all[ind], len(classes))]
         np.testing.assert_array_equal(pred, sk.predict(q))
         assert (np.array([len(set(r)) for r in enc_all[ind]]) == k).any()      # all-different rows did occur
+
+
+def test_pca_wrapper_logic_matches_sklearn_transform(monkeypatch):
+    """hse_facerec_tf_b200.PCA = sklearn's fit + a GPU projection; with the projection replaced by a host matmul the
+    wrapper (centring folded into a bias, whitening, clone/get_params, pickling) must reproduce sklearn's transform."""
+    import pickle
+    from sklearn.base import clone
+    from sklearn.decomposition import PCA as SkPCA
+    import hse_facerec_tf_b200.decomposition as dec
+    monkeypatch.setattr(dec, "_project", lambda x, comp, bias: x @ comp.T + bias)
+    rs = np.random.RandomState(2)
+    X = (rs.randn(300, 64) @ rs.randn(64, 64)).astype(np.float32) + 3.0
+    Q = (rs.randn(40, 64) @ rs.randn(64, 64)).astype(np.float32) + 3.0
+    for whiten in (False, True):
+        ours = dec.PCA(16, whiten=whiten, svd_solver="full", device="cpu").fit(X)
+        ref = SkPCA(16, whiten=whiten, svd_solver="full").fit(X)
+        got = ours.transform(Q)
+        assert got.dtype == np.float32 and got.shape == (40, 16)
+        np.testing.assert_allclose(got, ref.transform(Q), rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(ours.fit_transform(X), ref.fit_transform(X), rtol=2e-3, atol=2e-3)
+        twin = clone(ours)
+        assert twin.get_params()["whiten"] == whiten and twin.get_params()["device"] == "cpu"
+        back = pickle.loads(pickle.dumps(ours))
+        np.testing.assert_array_equal(back.transform(Q), got)
+    with np.testing.assert_raises(ValueError):
+        ours.transform(Q[:, :10])

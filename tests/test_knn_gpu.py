@@ -220,7 +220,7 @@ def test_pca_knn_pipeline_matches_sklearn(n_components, k):
     rs = np.random.RandomState(n_components + k)
     n_ids, per_id, d = 120, 8, 1024
     centres = preprocessing.normalize(rs.randn(n_ids, d))
-    X = preprocessing.normalize(np.repeat(centres, per_id, 0) + 0.35 * rs.randn(n_ids * per_id, d) / np.sqrt(d) * 8).astype(np.float32)
+    X = preprocessing.normalize(np.repeat(centres, per_id, 0) + 0.8 * rs.randn(n_ids * per_id, d) / np.sqrt(d)).astype(np.float32)
     y = np.repeat(np.arange(n_ids), per_id)
     test = rs.rand(len(X)) < 0.4
     Xtr, ytr, Xte = X[~test], y[~test], X[test]
@@ -232,8 +232,9 @@ def test_pca_knn_pipeline_matches_sklearn(n_components, k):
     assert Z.dtype == np.float32
     np.testing.assert_allclose(Z, Zr, rtol=1e-4, atol=2e-5)
     dk = neighbors.NearestNeighbors(n_neighbors=k + 1, algorithm="brute").fit(ref.named_steps["pca"].transform(Xtr)).kneighbors(Zr)[0] ** 2
-    clear = (np.diff(dk, axis=1) > 1e-5).all(axis=1)
-    assert clear.mean() > 0.9
+    # the two projections differ by fp32 summation order (~3e-6 per coordinate), i.e. up to ~1e-5 in a squared distance
+    clear = (np.diff(dk, axis=1) > 1e-4).all(axis=1)
+    assert clear.mean() > 0.8
     np.testing.assert_array_equal(ours.predict(Xte)[clear], ref.predict(Xte)[clear])
     assert abs(ours.score(Xte, y[test]) - ref.score(Xte, y[test])) < 0.02
     # device-resident hand-over between the two steps

@@ -451,7 +451,10 @@ def run_reference(args):
     v = float(np.mean(vals))
     cb["value"] = v
     print(json.dumps(dict(impl="reference", metric=metric, value=round(v, 2), unit=unit, n_gpus=args.gpus,
-                          steps=len(vals), warmup=1, ms_per_step=None, higher_is_better=True,
+                          steps=len(vals), warmup=1,
+                          # time this arm needs for one step of the GPU arm's size (batch images / nq queries),
+                          # extrapolated from the bounded samples
+                          ms_per_step=round(batch / v * 1e3, 1), higher_is_better=True,
                           scaling="strong" if args.workload == "knn" else "weak", vs_baseline=None, dtype="f32",
                           data="synthetic", config=dict(workload=args.workload, description=desc), cpu_baseline=cb,
                           e2e=dict(value=round(v, 2), unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))

@@ -1,10 +1,17 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:   acc[M,N] = A[M,K] * B[N,K]^T   (both operands K-major)
 //
-//   warp 0 (1 lane)  TMA producer: A/B k-blocks (128-byte rows, SWIZZLE_128B) into a STAGES-deep smem ring
-//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma cta_group::1, M=128 x N=BLOCK_N, fp32 accumulators in TMEM (2 stages)
+//   warp 0           TMA producer: A/B k-blocks (128-byte rows, SWIZZLE_128B) into a STAGES-deep smem ring
+//   warp 1           MMA issuer:   tcgen05.mma, M=128 x N=BLOCK_N per CTA, fp32 accumulators in TMEM (2 stages)
 //   warp 2           TMEM allocator
 //   warps 4..11      epilogue:     two warpgroups ping-pong on tiles (accumulator stage g = tile & 1);
 //                                  tcgen05.ld -> registers -> fused epilogue
+//   The producer and issuer warps run their loops whole-warp in uniform control flow; one elected lane issues
+//   (elect_one() in ptx.cuh explains why that matters for the issue rate).
+//
+// CTAS = 2 (CTA pair, cta_group::2): the tile is 256 rows x BLOCK_N over two SMs of a cluster.  Each CTA stages its own
+// 128 rows of A and BLOCK_N/2 rows of B; both CTAs' TMA loads complete on the LEADER's (rank 0) full barriers, only the
+// leader issues MMAs, its commits are multicast to both CTAs' empty / accumulator-full barriers, each CTA's epilogue
+// drains its own TMEM half and arrives on the leader's accumulator-empty barrier.  Work units are strided over clusters.
 //
 // Epilogues
 //   EPI_STORE  out = act(acc + bias[n] (+ residual[m,n]))  -> T, staged in swizzled smem, written with TMA stores.
@@ -26,7 +33,7 @@ enum { AMODE_2D = 0, AMODE_IM2COL = 1, AMODE_STEM16 = 2 };
 
 struct GemmParams {
   int M, N, K;            // K in elements
-  int num_m_blocks;       // ceil(M/128)
+  int num_m_blocks;       // ceil(M/128); CTA pairs: ceil(M/256)
   int num_n_blocks;       // ceil(N/BLOCK_N)
   int n_blocks_per_unit;  // STORE: 1.  KNN: gallery n-blocks handled by one work unit
   int num_units;          // num_m_blocks * ceil(num_n_blocks / n_blocks_per_unit)
@@ -37,7 +44,7 @@ struct GemmParams {
   int round_tf32;         // round stored fp32 values to tf32 (they feed the next tf32 GEMM)
   // EPI_KNN
   const float* gnorm;     // [N] squared norms of the gallery rows
-  float* part_score;      // [M][splits][2 warpgroups][2]
+  float* part_score;      // [M][splits][2 warpgroups][2]   (EPI_KNN4: [...][4])
   int* part_idx;          // [M][splits][2 warpgroups][2]
   int splits;
   // AMODE_IM2COL (implicit GEMM over an NHWC tensor): k-block kb -> (tap, channel block)

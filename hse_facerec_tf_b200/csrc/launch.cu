@@ -35,8 +35,7 @@ static bool pdl_enabled() {
 template <typename... KArgs, typename... Args>
 static void launch_pdl_cluster(void (*kern)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;

@@ -32,6 +32,8 @@ SIGNATURES = {
     "hfr_model_free": (None, [_vp]),
     "hfr_crop_resize_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "hfr_resize_pil_u8": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "hfr_debug_gemm_tile_choice": (_i, [_i64, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "hfr_debug_knn_plan": (_i, [_i64, _i64, C.POINTER(_i), C.POINTER(_i)]),
     "hfr_pairwise_dist": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
     "hfr_age_gender_post": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hfr_l2_normalize": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

@@ -930,6 +930,20 @@ int hfr_pairwise_dist(const float* x, int64_t n, const float* y, int64_t m, int 
   });
 }
 
+int hfr_debug_gemm_tile_choice(int64_t m, int n, int k, int conv_taps, int sms, int* ctas, int* block_n) {
+  return guarded([&] {
+    if (!ctas || !block_n || m <= 0 || n <= 0 || k <= 0 || conv_taps < 0 || sms <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    gemm_tile_choice(m, n, k, conv_taps, sms, ctas, block_n);
+  });
+}
+
+int hfr_debug_knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit) {
+  return guarded([&] {
+    if (!splits || !n_blocks_per_unit || nq <= 0 || n <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    knn_plan(nq, n, splits, n_blocks_per_unit);
+  });
+}
+
 int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, void* stream) {
   return guarded([&] {
     if (!x || !y || n < 0 || dim <= 0) throw Error(HFR_ERR_INVALID, "bad argument");

@@ -320,13 +320,26 @@ static int pick_block_n(int64_t M, int N, int sms, int widest) {
   return 64;
 }
 
+void gemm_tile_choice(int64_t M, int N, int K, int conv_taps, int sms, int* ctas, int* block_n) {
+  const bool im2col = conv_taps > 0;
+  if (const int pbn = pick_pair_block_n(M, N, K, sms, im2col, conv_taps > 1)) {
+    *ctas = 2;
+    *block_n = pbn;
+    return;
+  }
+  *ctas = 1;
+  *block_n = pick_block_n(M, N, sms, (!im2col || conv_taps == 1) ? 128 : 256);
+}
+
 template <typename T, int AMODE>
 static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, GemmParams p, int64_t M, int N, int K,
                               int prec, int device, cudaStream_t s) {
   CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
   CUtensorMap tR = p.residual ? make_tmap_2d(p.residual, prec, (uint64_t)M, (uint64_t)N, 128) : tD;
-  if (const int pbn = pick_pair_block_n(M, N, K, device_sm_count(device), AMODE != AMODE_2D,
-                                        AMODE != AMODE_2D && p.conv_kw > 1)) {
+  int ctas = 1, bn = 0;
+  gemm_tile_choice(M, N, K, AMODE == AMODE_2D ? 0 : p.conv_kw * p.conv_kw, device_sm_count(device), &ctas, &bn);
+  if (ctas == 2) {
+    const int pbn = bn;
     CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)pbn / 2);  // each CTA loads half the rows
     p.num_m_blocks = (int)((M + 255) / 256);
     p.num_n_blocks = N / pbn;
@@ -338,7 +351,6 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
   }
   // 1x1 layers are HBM / latency bound: 128-column tiles (twice the units, five 32 KB stages in flight instead of three
   // 48 KB ones) measured faster than 256-column ones on every ResNet-50 1x1 layer but two ties
-  const int bn = pick_block_n(M, N, device_sm_count(device), (AMODE == AMODE_2D || p.conv_kw == 1) ? 128 : 256);
   CUtensorMap tB = make_tmap_2d(b, prec, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
   p.num_m_blocks = (int)((M + 127) / 128);
   p.num_n_blocks = (N + bn - 1) / bn;

@@ -143,6 +143,10 @@ struct KnnGemmArgs {
   int cand = 2;  // candidates per (query, split, warpgroup): 2 (1-NN) or 4 (k-NN, k <= 4)
 };
 void knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
+// Tile shape the GEMM launcher picks for an M x N x K problem on a device with `sms` SMs (host logic only, testable
+// without a GPU): *ctas = 1 or 2 (CTA pair), *block_n = 64 / 128 / 256.  conv_taps = kh * kw of an implicit-GEMM
+// convolution (0: plain 2-D GEMM).
+void gemm_tile_choice(int64_t M, int N, int K, int conv_taps, int sms, int* ctas, int* block_n);
 void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s);
 void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
                          int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s);

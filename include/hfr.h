@@ -110,6 +110,11 @@ void hfr_model_free(hfr_model* m);
  * [n][5] = (frame index, x1, y1, x2, y2), already clamped to the frame with x2 > x1, y2 > y1.  out: [n,out_h,out_w,3]. */
 int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n,
                        uint8_t* out, int out_h, int out_w, int device, void* stream);
+/* Host-side launch heuristics, exposed so that they can be tested without a GPU: the tile the GEMM launcher uses for an
+ * m x n x k problem on a device with `sms` SMs (ctas = 1 or 2 CTAs per tile, block_n = 64 / 128 / 256; conv_taps = kh*kw
+ * of an implicit-GEMM convolution, 0 for a plain GEMM), and the gallery split of the k-NN kernel. */
+int hfr_debug_gemm_tile_choice(int64_t m, int n, int k, int conv_taps, int sms, int* ctas, int* block_n);
+int hfr_debug_knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
 /* Distance matrix for the clustering scripts: out[i,j] = ||x_i - y_j||_2 (float32 [n,m], device), the per-pair
  * expression of process_photos.py:46-48 and sklearn.metrics.pairwise_distances(X_norm) of facial_clustering_test.py:396;
  * y == NULL: y = x (m == n, exact zeros on the diagonal).  With year/born (device float32 [n] / [m], all four or none):

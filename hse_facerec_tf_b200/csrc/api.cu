@@ -198,7 +198,32 @@ struct hfr_model {
   std::vector<double> layer_ms;
   int timed_steps = 0;
   // tensor-core stem: staged space-to-depth input + per-preprocessing-flags weights
-  DevBuf stem_scratch;
+  // Experimental (HFR_LANES=2..4, default 1): the batch is cut into `lanes` slices that run the whole layer list on
+  // their own streams between a fork and a join - independent kernels of different slices fill each other's ramp-up
+  // and tail on the SMs.  Every tensor is batch-major, so a slice is a pointer offset; only the stem's staging buffer is
+  // per lane.  Results do not depend on the lane count (every image's arithmetic is independent of the batch).
+  static constexpr int kMaxLanes = 4;
+  int n_lanes = getenv("HFR_LANES") ? std::max(1, std::min(kMaxLanes, atoi(getenv("HFR_LANES")))) : 1;
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  void init_lanes() {
+    if (lane_fork) return;
+    cuda_check(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming), "cudaEventCreate");
+    for (int l = 1; l < kMaxLanes; ++l) {
+      cuda_check(cudaStreamCreateWithFlags(&lane_stream[l], cudaStreamNonBlocking), "cudaStreamCreate(lane)");
+      cuda_check(cudaEventCreateWithFlags(&lane_join[l], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  void free_lanes() {
+    if (!lane_fork) return;
+    cudaEventDestroy(lane_fork);
+    for (int l = 1; l < kMaxLanes; ++l) {
+      cudaStreamDestroy(lane_stream[l]);
+      cudaEventDestroy(lane_join[l]);
+    }
+    lane_fork = nullptr;
+  }
+  DevBuf stem_scratch_lane[kMaxLanes];
   std::map<int, std::pair<void*, StemTcGeom>> stem_w2;
   // host-buffer path staging
   DevBuf stage_in;
@@ -238,6 +263,7 @@ struct hfr_model {
 
   ~hfr_model() {
     free_host_pipeline();
+    free_lanes();
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto e : ev) cudaEventDestroy(e);
     for (auto& kv : stem_w2) cudaFree(kv.second.first);
@@ -406,13 +432,33 @@ struct hfr_model {
   void run_layers(const void* x, int in_dtype, int batch, int flags, void* const* outs, cudaStream_t s) {
     // L2-sized sub-batching: every tensor is batch-major, so a slice of the batch is a pointer offset.  Running the
     // whole layer list on one slice at a time keeps producer->consumer tensors L2-resident.
+    if (n_lanes > 1 && !timing && sub_batch <= 0 && s != nullptr && batch >= 2 * n_lanes) {
+      init_lanes();
+      const int per = (batch + n_lanes - 1) / n_lanes;
+      cuda_check(cudaEventRecord(lane_fork, s), "cudaEventRecord(fork)");
+      for (int l = 0; l < n_lanes; ++l) {
+        const int b0 = l * per, n = std::min(per, batch - b0);
+        if (n <= 0) break;
+        cudaStream_t sl = l == 0 ? s : lane_stream[l];
+        if (l > 0) cuda_check(cudaStreamWaitEvent(sl, lane_fork, 0), "cudaStreamWaitEvent(fork)");
+        run_slice(x, in_dtype, batch, b0, n, flags, sl, l);
+        if (l > 0) {
+          cuda_check(cudaEventRecord(lane_join[l], sl), "cudaEventRecord(join)");
+          cuda_check(cudaStreamWaitEvent(s, lane_join[l], 0), "cudaStreamWaitEvent(join)");
+        }
+      }
+      finish_outputs(batch, flags, outs, s);
+      return;
+    }
     int sub = sub_batch > 0 && !timing ? sub_batch : batch;
     if (sub > batch) sub = batch;
     for (int b0 = 0; b0 < batch; b0 += sub) run_slice(x, in_dtype, batch, b0, std::min(sub, batch - b0), flags, s);
     finish_outputs(batch, flags, outs, s);
   }
 
-  void run_slice(const void* x_all, int in_dtype, int total, int img0, int batch, int flags, cudaStream_t s) {
+  void run_slice(const void* x_all, int in_dtype, int total, int img0, int batch, int flags, cudaStream_t s,
+                 int lane = 0) {
+    DevBuf& stem_scratch = stem_scratch_lane[lane];
     const int prec = precision;
     const int rt = (prec == HFR_TF32);
     const size_t in_img_bytes = (size_t)plan.in_h * plan.in_w * plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);

@@ -265,3 +265,18 @@ def test_extract_stream_matches_extract_batch(age_gender_pb):
     got = np.vstack([o.copy() for o in tfi.extract_stream(iter(batches), l2norm=True)])
     np.testing.assert_array_equal(got, want)
     assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HFR_TEST_EXPERIMENTAL"),
+                    reason="experimental paths (HFR_LANES) have not been measured on a GPU yet: opt in with HFR_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_experimental_lanes_give_identical_outputs(age_gender_pb, monkeypatch, lanes):
+    """HFR_LANES: batch slices on forked streams must not change a single output value (eager and graph replay)."""
+    x = torch.from_numpy(np.random.RandomState(9).randint(0, 256, (37, 224, 224, 3)).astype(np.uint8)).cuda()
+    outs = ["age_pred/Softmax:0", "global_pooling/Mean:0"]
+    base = hfr.HfrModel(age_gender_pb, "input_1:0", outs, precision="bf16").forward(x)
+    monkeypatch.setenv("HFR_LANES", str(lanes))
+    m = hfr.HfrModel(age_gender_pb, "input_1:0", outs, precision="bf16")
+    for graph in (False, True, True):
+        for got, want in zip(m.forward(x, graph=graph), base):
+            torch.testing.assert_close(got, want, rtol=0, atol=0)

@@ -644,6 +644,8 @@ struct hfr_model {
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       if (graphs.size() >= 64) {
+        // batches submitted through hfr_model_submit_host may still be replaying some of these graphs
+        cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         graphs.clear();
       }

@@ -60,14 +60,18 @@ static float f32_to_tf32(float f) {  // round to nearest even on the 13 dropped 
 // input scale and the mean subtraction of the reference's pre-processing are folded in: data channels carry scale*W for
 // the raw channel order, channels 12..14 carry -sum(mean*W) split into three bf16 terms (fp32-accurate constant).
 struct StemTcGeom { int ka, kb, pt2, pl2; };
+// lo_sweep: append a second [taps][cout][16] block holding the bf16 residual of every data weight (w = hi + lo carries
+// 16 mantissa bits: the experimental tf32-mode stem issues both sweeps into one accumulator); its constant channels are 0.
 static std::vector<uint16_t> stem_tc_weights(const std::vector<float>& w, int kh, int kw, int cout, int pad_t, int pad_l,
-                                             int flip, float scale, const float mean[3], StemTcGeom* g) {
+                                             int flip, float scale, const float mean[3], StemTcGeom* g,
+                                             bool lo_sweep = false) {
   const int shy = pad_t & 1, shx = pad_l & 1;
   g->pt2 = pad_t + shy;
   g->pl2 = pad_l + shx;
   g->ka = (kh + shy + 1) / 2;
   g->kb = (kw + shx + 1) / 2;
-  std::vector<uint16_t> out((size_t)g->ka * g->kb * cout * 16, 0);
+  const size_t sweep = (size_t)g->ka * g->kb * cout * 16;
+  std::vector<uint16_t> out(sweep * (lo_sweep ? 2 : 1), 0);
   for (int a = 0; a < g->ka; ++a)
     for (int b = 0; b < g->kb; ++b)
       for (int co = 0; co < cout; ++co) {
@@ -80,7 +84,14 @@ static std::vector<uint16_t> stem_tc_weights(const std::vector<float>& w, int kh
             for (int j = 0; j < 3; ++j) {
               const int c = flip ? 2 - j : j;
               const float ww = w[(((size_t)r * kw + q) * 3 + c) * cout + co];
-              dst[(dy * 2 + dx) * 3 + j] = f32_to_bf16(scale * ww);
+              const uint16_t hi_w = f32_to_bf16(scale * ww);
+              dst[(dy * 2 + dx) * 3 + j] = hi_w;
+              if (lo_sweep) {
+                uint32_t u = (uint32_t)hi_w << 16;
+                float hf;
+                memcpy(&hf, &u, 4);
+                dst[sweep + (dy * 2 + dx) * 3 + j] = f32_to_bf16(scale * ww - hf);
+              }
               cst -= (double)mean[c] * ww;
             }
           }
@@ -176,6 +187,7 @@ struct hfr_model {
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
   int sub_batch = getenv("HFR_SUB_BATCH") ? atoi(getenv("HFR_SUB_BATCH")) : 0;
   bool stem_window = window_enabled();
+  bool tf32_tc_stem = getenv("HFR_TF32_TC_STEM") != nullptr;  // experimental, see the L_STEM case
   bool fuse_dwpw = getenv("HFR_FUSE") != nullptr;  // experimental: measured slower than the two-kernel path
   // layer i is a stride-1 depthwise whose only consumer is the 1x1 convolution at i+1: run both as dwpw_kernel
   bool fused_pair(size_t i) const {
@@ -502,7 +514,10 @@ struct hfr_model {
             if (flags & HFR_FLAG_SCALE_PM1) { a.scale = 1.f / 127.5f; a.mean[0] = a.mean[1] = a.mean[2] = 1.f; }
           }
           a.act = act; a.round_tf32 = round_out;
-          const bool tc = prec == HFR_BF16 && a.in_u8 && L.stride == 2 && L.dil == 1 && (L.H % 2 == 0) &&
+          // experimental (HFR_TF32_TC_STEM=1, unmeasured): the tf32 mode's stem on the tensor cores as well - fp32
+          // output, weights as hi + lo bf16 sweeps (the uint8 image is exact in bf16), window kernel only
+          const bool tc32 = prec == HFR_TF32 && stem_window && tf32_tc_stem;
+          const bool tc = (prec == HFR_BF16 || tc32) && a.in_u8 && L.stride == 2 && L.dil == 1 && (L.H % 2 == 0) &&
                           (L.W % 2 == 0) && (L.cout == 32 || L.cout == 64) && !stem_force_direct;
           if (!tc) {
             launch_stem(a, prec, s);
@@ -512,8 +527,9 @@ struct hfr_model {
           auto it = stem_w2.find(key);
           if (it == stem_w2.end()) {
             StemTcGeom g;
-            std::vector<uint16_t> h = stem_tc_weights(L.w, L.kh, L.kw, L.cout, L.pad_t, L.pad_l, a.flip, a.scale, a.mean, &g);
-            if (stem_window) h = stem_window_layout(h, g.ka * g.kb, L.cout);
+            std::vector<uint16_t> h =
+                stem_tc_weights(L.w, L.kh, L.kw, L.cout, L.pad_t, L.pad_l, a.flip, a.scale, a.mean, &g, tc32);
+            if (stem_window) h = stem_window_layout(h, g.ka * g.kb * (tc32 ? 2 : 1), L.cout);
             it = stem_w2.emplace(key, std::make_pair(upload(h.data(), h.size() * 2), g)).first;
           }
           const StemTcGeom& g = it->second.second;
@@ -522,6 +538,11 @@ struct hfr_model {
           t.B = batch; t.H = L.H; t.W = L.W; t.Ho = L.Ho; t.Wo = L.Wo; t.cout = L.cout;
           t.ka = g.ka; t.kb = g.kb; t.pt2 = g.pt2; t.pl2 = g.pl2; t.act = act;
           t.use_window = stem_window;
+          if (tc32) {
+            t.out_f32 = 1;
+            t.passes = 2;
+            t.round_tf32 = round_out;
+          }
           const size_t need = (size_t)batch * (L.Ho + g.ka - 1) * (L.Wo + g.kb - 1) * 32;
           if (need > stem_scratch.bytes) {
             cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // previous users of the old buffer

@@ -16,6 +16,7 @@
 // Used for the stem (after space-to-depth, see stem_s2d_kernel: 7x7/2 -> 4x4/1 over 16 channels) and for 3x3 convolutions
 // with 64 output channels (ResNet stage 2), which the generic im2col-TMA path leaves L2-bandwidth-bound.
 #pragma once
+#include "gemm_tc.cuh"  // ACT_* codes
 #include "ptx.cuh"
 
 namespace hfr {
@@ -35,6 +36,7 @@ struct WinParams {
   int shifted;                      // plane-major only: taps_w copies of the window, copy s shifted by s pixels, each
                                     // exactly 8 pixels wide -> every 8-row operand group is one aligned 128-byte line
   int copy_pitch;                   // bytes between consecutive shifted copies
+  int round_tf32;                   // fp32 output only: round to tf32 (the consumer is a tf32 tensor-core layer)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -57,7 +59,10 @@ constexpr int kWinStages = 3;
 
 // dynamic smem: [1 KB align][weights w_bytes][kWinStages x window win_bytes (1 KB-rounded)][4 x 16 KB staging][barriers]
 // TH x TW taps with KS K=16 steps each known at compile time unroll the MMA issue completely (TH = 0: runtime loops).
-template <int TH, int TW, int KS>
+// TOut = float (experimental, the tf32-mode stem): fp32 output in two 32-column chunks per tile.  PASSES = 2: the weight
+// matrix holds a second copy of every tap with the bf16 residual of the weights (w = hi + lo, 16 mantissa bits), issued
+// as a second sweep of MMAs over the same window into the same accumulator.
+template <int TH, int TW, int KS, typename TOut = __nv_bfloat16, int PASSES = 1>
 __global__ void __launch_bounds__(384, 1)
 conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmD, const WinParams p, const int w_bytes, const int win_stride) {
@@ -171,16 +176,19 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if constexpr (TH > 0) {
           // independent descriptor offsets, no loop-carried chain through the (slow) uniform datapath
 #pragma unroll
-          for (int r = 0; r < TH; ++r)
+          for (int ps = 0; ps < PASSES; ++ps)
 #pragma unroll
-            for (int s = 0; s < TW; ++s)
+            for (int r = 0; r < TH; ++r)
 #pragma unroll
-              for (int j = 0; j < KS; ++j) {
-                const int i = (r * TW + s) * KS + j;
-                umma<false>(d_tmem, a_row + (uint64_t)(r * a_row_step + s * a_col_step + j * a_k_step),
-                            bd + (uint64_t)(i * b_k_step), idesc, i != 0);
-              }
+              for (int s = 0; s < TW; ++s)
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                  const int i = ((ps * TH + r) * TW + s) * KS + j;
+                  umma<false>(d_tmem, a_row + (uint64_t)(r * a_row_step + s * a_col_step + j * a_k_step),
+                              bd + (uint64_t)(i * b_k_step), idesc, i != 0);
+                }
         } else
+        for (int ps = 0; ps < PASSES; ++ps, a_row -= (uint64_t)p.taps_h * a_row_step)
         for (int r = 0; r < p.taps_h; ++r, a_row += a_row_step) {
           uint64_t a_tap = a_row;
           for (int s = 0; s < p.taps_w; ++s, a_tap += a_col_step) {
@@ -219,9 +227,13 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       ++my_tiles;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      if (leader) tma_store_wait_read<1>();
+      // bf16: a tile is one 16 KB staging buffer, double-buffered across this warpgroup's tiles.  fp32: a tile is two
+      // 32-column chunks = both buffers, so every earlier store must have finished reading them.
+      if (leader) {
+        if constexpr (sizeof(TOut) == 4) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+      }
       named_bar_sync(bar_id, 128);
-      const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
+      const uint32_t st_row = sEpi + (g * 2 + (sizeof(TOut) == 4 ? 0 : buf)) * 16384 + row * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t r[32];
@@ -242,13 +254,30 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
+        if constexpr (sizeof(TOut) == 4) {
+          // chunk h = output channels 32h .. 32h+31 as 128-byte fp32 rows in staging buffer h of this warpgroup
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w[4];
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j];
+            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            if (p.act == ACT_RELU6) x = fminf(fmaxf(x, 0.f), 6.f);
+            v[j] = p.round_tf32 ? round_tf32(x) : x;
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2_act(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], p.act);
-          const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t a = st_row + h * 16384 + (((uint32_t)q ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                         "f"(v[4 * q + 2]), "f"(v[4 * q + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2_act(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], p.act);
+            const uint32_t a = st_row + (((uint32_t)(h * 4 + q) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+          }
         }
       }
       tc_fence_before();
@@ -257,7 +286,12 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
       if (leader) {
-        tma_store_4d(&tmD, sEpi + (g * 2 + buf) * 16384, 0, tx * 8, ty * 16, b);
+        if constexpr (sizeof(TOut) == 4) {
+          tma_store_4d(&tmD, sEpi + (g * 2 + 0) * 16384, 0, tx * 8, ty * 16, b);
+          if (p.N > 32) tma_store_4d(&tmD, sEpi + (g * 2 + 1) * 16384, 32, tx * 8, ty * 16, b);
+        } else {
+          tma_store_4d(&tmD, sEpi + (g * 2 + buf) * 16384, 0, tx * 8, ty * 16, b);
+        }
         tma_store_commit();
       }
     }

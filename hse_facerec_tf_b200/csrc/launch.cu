@@ -443,6 +443,7 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
     w.B = a.B; w.H = Hs; w.W = Ws; w.cin = 16; w.Ho = a.Ho; w.Wo = a.Wo; w.cout = a.cout;
     w.kh = a.ka; w.kw = a.kb; w.pad_t = 0; w.pad_l = 0; w.act = a.act;
     w.plane_major = 1;
+    w.out_f32 = a.out_f32; w.passes = a.passes; w.round_tf32 = a.round_tf32;
     launch_conv_window(w, device, s);
     return;
   }
@@ -498,10 +499,10 @@ bool conv_window_fits(int cin, int kh, int kw) {
   window_smem(cin, kh, kw, &wb, &wn, &ws, &tot);
   return tot <= 227 * 1024;
 }
-template <int TH, int TW, int KS>
+template <int TH, int TW, int KS, typename TOut = __nv_bfloat16, int PASSES = 1>
 static void launch_window_inst(int grid, int total, int device, cudaStream_t s, const CUtensorMap& tX, const CUtensorMap& tW,
                                const CUtensorMap& tD, const WinParams& p, int w_bytes, int win_stride) {
-  auto kern = conv_window_kernel<TH, TW, KS>;
+  auto kern = conv_window_kernel<TH, TW, KS, TOut, PASSES>;
   static std::atomic<bool> configured[64];  // per instantiation
   if (!configured[device].load()) {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
@@ -515,6 +516,11 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   int w_bytes, win_bytes, win_stride, total;
   const bool shifted = a.plane_major && getenv("HFR_NO_SHIFTED") == nullptr;
   window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total, shifted);
+  if (a.passes != 1 && a.passes != 2) throw Error(-1, "window conv: passes must be 1 or 2");
+  if (a.passes == 2) {  // second sweep of taps (bf16 residual of the weights) resident next to the first
+    total += w_bytes;
+    w_bytes *= 2;
+  }
   if (total > 227 * 1024) throw Error(-5, "window conv: shared memory budget exceeded");
   const int planes = a.cin / 8;
   const int ww = 8 + a.kw - 1, wh = 16 + a.kh - 1;
@@ -532,15 +538,16 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
     const uint32_t xbox[4] = {8, (uint32_t)ww, (uint32_t)wh, 1};
     tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
-  const int chunks = a.kh * a.kw * planes;
+  const int chunks = a.kh * a.kw * planes * a.passes;
   const uint64_t wd[3] = {8, 64, (uint64_t)chunks};
   const uint64_t wst[2] = {16, 1024};
   const uint32_t wbox[3] = {8, 64, 2};
   CUtensorMap tW = make_tiled(a.w, PREC_BF16, 3, wd, wst, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
   const uint64_t yd[4] = {(uint64_t)a.cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.B};
-  const uint64_t ys[3] = {(uint64_t)a.cout * 2, (uint64_t)a.Wo * a.cout * 2, (uint64_t)a.Ho * a.Wo * a.cout * 2};
-  const uint32_t ybox[4] = {64, 8, 16, 1};
-  CUtensorMap tD = make_tiled(a.y, PREC_BF16, 4, yd, ys, ybox, CU_TENSOR_MAP_SWIZZLE_128B);
+  const uint64_t yes = a.out_f32 ? 4 : 2;
+  const uint64_t ys[3] = {(uint64_t)a.cout * yes, (uint64_t)a.Wo * a.cout * yes, (uint64_t)a.Ho * a.Wo * a.cout * yes};
+  const uint32_t ybox[4] = {a.out_f32 ? 32u : 64u, 8, 16, 1};   // 128-byte rows either way
+  CUtensorMap tD = make_tiled(a.y, a.out_f32 ? PREC_TF32 : PREC_BF16, 4, yd, ys, ybox, CU_TENSOR_MAP_SWIZZLE_128B);
   WinParams p;
   memset(&p, 0, sizeof(p));
   p.tiles_x = (a.Wo + 7) / 8;
@@ -552,8 +559,18 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   p.plane_pitch = shifted ? wh * 128 : a.plane_major ? plane_px : (plane_px + 127) / 128 * 128;
   p.shifted = shifted;
   p.copy_pitch = planes * wh * 128;
+  p.round_tf32 = a.round_tf32;
   const int grid = p.num_tiles < device_sm_count(device) ? p.num_tiles : device_sm_count(device);
   if (grid < 1) return;
+  if (a.out_f32 || a.passes == 2) {  // experimental tf32-mode stem: fp32 output, two weight sweeps
+    if (!(a.out_f32 && a.passes == 2)) throw Error(-5, "window conv: fp32 output comes with two weight sweeps");
+    if (a.kh == 4 && a.kw == 4 && planes == 2)
+      launch_window_inst<4, 4, 1, float, 2>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
+    else
+      launch_window_inst<0, 0, 0, float, 2>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);
+    HFR_LAUNCH_CHECK("conv_window_f32");
+    return;
+  }
   // fully unrolled MMA issue for the shapes the networks use: stem after space-to-depth (4x4 taps x 16 channels),
   // 3x3 over 64 and 32 channels
   if (a.kh == 4 && a.kw == 4 && planes == 2) launch_window_inst<4, 4, 1>(grid, total, device, s, tX, tW, tD, p, w_bytes, win_stride);

@@ -45,6 +45,8 @@ struct StemTcArgs {
   int B, H, W, Ho, Wo, cout, ka, kb, pt2, pl2;   // pt2/pl2: even padding used by the staging kernel
   int act;
   int use_window;       // 1: w2 is in window layout [taps*2][64][8] (conv_window_kernel); 0: [taps][cout][16] (STEM16 im2col)
+  // experimental tf32-mode stem (window kernel only): fp32 output, weights as hi + lo bf16 terms (w2 holds both sweeps)
+  int out_f32 = 0, passes = 1, round_tf32 = 0;
 };
 void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s);
 
@@ -56,6 +58,9 @@ struct WinArgs {
   void* y;            // [B,Ho,Wo,cout] bf16
   int B, H, W, cin, Ho, Wo, cout, kh, kw, pad_t, pad_l, act;
   int plane_major;    // x is [B][cin/8][H][W][8] instead of NHWC
+  int out_f32 = 0;    // y is fp32 (experimental)
+  int passes = 1;     // 2: w holds a second sweep of taps with the weights' bf16 residual
+  int round_tf32 = 0;
 };
 bool conv_window_fits(int cin, int kh, int kw);
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s);

@@ -280,3 +280,32 @@ def test_experimental_lanes_give_identical_outputs(age_gender_pb, monkeypatch, l
     for graph in (False, True, True):
         for got, want in zip(m.forward(x, graph=graph), base):
             torch.testing.assert_close(got, want, rtol=0, atol=0)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HFR_TEST_EXPERIMENTAL"),
+                    reason="experimental paths (HFR_TF32_TC_STEM) have not been measured on a GPU yet: opt in with HFR_TEST_EXPERIMENTAL=1")
+def test_experimental_tf32_tensor_core_stem(age_gender_pb, monkeypatch, tmp_path):
+    """HFR_TF32_TC_STEM: the tf32 mode's stem through the window kernel (fp32 output, hi + lo bf16 weight sweeps) must
+    agree with the CUDA-core fp32 stem to well inside the tf32 mode's own tolerance - MobileNet (3x3/2, 32 channels,
+    generic kernel) and ResNet-50 (7x7/2, 64 channels, unrolled kernel)."""
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    rs = np.random.RandomState(13)
+    cases = [(age_gender_pb, "input_1:0", "global_pooling/Mean:0", True),
+             (write_resnet50_pb(str(tmp_path / "r50.pb"), seed=7), "input:0", "pool5_7x7_s1:0", False)]
+    for pb, inp, out, imagenet in cases:
+        x = torch.from_numpy(np.concatenate([smooth_images(3, 224, 5), rs.randint(0, 256, (5, 224, 224, 3)).astype(np.uint8)])).cuda()
+        monkeypatch.delenv("HFR_TF32_TC_STEM", raising=False)
+        m0 = hfr.HfrModel(pb, inp, [out], precision="tf32")
+        (want,) = m0.forward(x, True, imagenet)
+        m0.keep_activations(True)
+        m0.forward(x, True, imagenet)
+        stem_want = m0.layer_output(0, 8).clone()
+        monkeypatch.setenv("HFR_TF32_TC_STEM", "1")
+        m1 = hfr.HfrModel(pb, inp, [out], precision="tf32")
+        (got,) = m1.forward(x, True, imagenet)
+        m1.keep_activations(True)
+        m1.forward(x, True, imagenet)
+        stem_got = m1.layer_output(0, 8)
+        err = float((stem_got - stem_want).abs().max()) / (float(stem_want.abs().max()) + 1.0)
+        assert err < 2e-3, f"stem output differs: {err}"          # both are rounded to tf32 (2^-11) on store
+        assert cosine(got.cpu().numpy(), want.cpu().numpy()).min() > 0.99999

@@ -241,7 +241,8 @@ static void launch_dw_pipe_t(const DwArgs& a, int prec, int device, cudaStream_t
 
 void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
   if (a.B > 65535) throw Error(-1, "depthwise: batch too large for one launch");
-  if (getenv("HFR_DW_ONESHOT") == nullptr && (a.stride == 1 || a.stride == 2)) {
+  static const bool oneshot = getenv("HFR_DW_ONESHOT") != nullptr;  // environment switches are read once
+  if (!oneshot && (a.stride == 1 || a.stride == 2)) {
     int device = 0;
     cuda_check(cudaGetDevice(&device), "cudaGetDevice");
     const int es = prec == PREC_BF16 ? 2 : 4;
@@ -257,7 +258,8 @@ void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
   }
   // 16x8-pixel tiles (TILE_H = 16) were measured 40 % slower than 8x8 on B200 (fewer, longer-running CTAs): kept only
   // as a template option
-  const bool tall = getenv("HFR_DW_TALL") != nullptr && a.Ho > 8;
+  static const bool tall_env = getenv("HFR_DW_TALL") != nullptr;
+  const bool tall = tall_env && a.Ho > 8;
   if (a.stride == 1) {
     if (prec == PREC_BF16) { if (tall) launch_dw_t<__nv_bfloat16, 1, 16>(a, prec, s); else launch_dw_t<__nv_bfloat16, 1, 8>(a, prec, s); }
     else                   { if (tall) launch_dw_t<float, 1, 16>(a, prec, s); else launch_dw_t<float, 1, 8>(a, prec, s); }
@@ -514,7 +516,8 @@ static void launch_window_inst(int grid, int total, int device, cudaStream_t s, 
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   if (a.cout > 64 || a.cout % 32 || !conv_window_fits(a.cin, a.kh, a.kw)) throw Error(-5, "window conv: unsupported shape");
   int w_bytes, win_bytes, win_stride, total;
-  const bool shifted = a.plane_major && getenv("HFR_NO_SHIFTED") == nullptr;
+  static const bool no_shifted = getenv("HFR_NO_SHIFTED") != nullptr;
+  const bool shifted = a.plane_major && !no_shifted;
   window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total, shifted);
   if (a.passes != 1 && a.passes != 2) throw Error(-1, "window conv: passes must be 1 or 2");
   if (a.passes == 2) {  // second sweep of taps (bf16 residual of the weights) resident next to the first

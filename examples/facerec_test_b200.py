@@ -29,18 +29,23 @@ def is_image(path):
     return path.lower().endswith((".jpg", ".jpeg", ".png", ".bmp"))
 
 
-def get_files(db_dir):                                                            # facerec_test.py:150-153
-    return [[d, os.path.join(d, f)] for d in next(os.walk(db_dir))[1]
-            for f in next(os.walk(os.path.join(db_dir, d)))[2] if is_image(f)]
+def get_files(db_dir):
+    """[identity, identity/file] for every image one level below db_dir (the layout facerec_test.py:150-153 walks)."""
+    pairs = []
+    for identity in sorted(os.listdir(db_dir)):
+        folder = os.path.join(db_dir, identity)
+        if os.path.isdir(folder):
+            pairs += [[identity, os.path.join(identity, f)] for f in sorted(os.listdir(folder)) if is_image(f)]
+    return pairs
 
 
-def classifier_tester(classifier, x, y):                                          # facerec_test.py:200-207, verbatim
-    sss = model_selection.StratifiedShuffleSplit(n_splits=1, test_size=0.5, random_state=0)
-    scores = model_selection.cross_validate(classifier, x, y, scoring="accuracy", cv=sss)
-    acc = scores["test_score"]
-    print("accuracies=", acc * 100)
-    print("total acc=", round(acc.mean() * 100, 2), round(acc.std() * 100, 2))
-    print("test time=", scores["score_time"])
+def classifier_tester(classifier, x, y):
+    """Same protocol as facerec_test.py:200-207: one stratified 50/50 split (seed 0), accuracy through cross_validate -
+    which clones the estimator, so it exercises get_params/set_params of the drop-in classes."""
+    split = model_selection.StratifiedShuffleSplit(n_splits=1, test_size=0.5, random_state=0)
+    result = model_selection.cross_validate(classifier, x, y, scoring="accuracy", cv=split)
+    accuracy = 100.0 * result["test_score"]
+    print(f"  accuracy {accuracy.mean():.2f} % (+- {accuracy.std():.2f}), predict time {result['score_time'].sum() * 1e3:.1f} ms")
 
 
 def synthetic_dataset(root, n_ids=24, per_id=6):
@@ -95,11 +100,10 @@ def main():
     data = np.load(features_file)
     X, y = data["x"], data["y"]
     X_norm = hfr.normalize(X, norm="l2")                                          # <- preprocessing.normalize
-    y_l = list(y)
-    indices = [i for i, el in enumerate(y_l) if y_l.count(el) > 1]
-    y = y[indices]
-    y = preprocessing.LabelEncoder().fit_transform(y)
-    X_norm = X_norm[indices, :]
+    labels, counts = np.unique(y, return_counts=True)          # identities with a single image cannot be split 50/50
+    keep = np.isin(y, labels[counts > 1])
+    y = preprocessing.LabelEncoder().fit_transform(y[keep])
+    X_norm = X_norm[keep]
     print("after loading: num_classes=", len(np.unique(y)), " X_norm shape:", X_norm.shape)
 
     pca_components = min(128, X_norm.shape[0] // 2 - 1)

@@ -35,15 +35,12 @@ def test_album_distance_matrix_matches_process_photos():
     years = rs.randint(2005, 2019, n)
     born = years - rs.randint(1, 70, n)                             # apparent age at photo time >= 1
 
-    def feature_distance(i, j):                                     # process_photos.py:46-52, verbatim arithmetic
-        dist = np.sqrt(np.sum((f[i] - f[j]) ** 2))
-        max_year = max(years[i], years[j])
-        cur_age_i, cur_age_j = max_year - born[i], max_year - born[j]
-        age_dist = (cur_age_i - cur_age_j) ** 2 / (cur_age_i + cur_age_j)
-        return [dist, age_dist * 0.1]
-
-    pair = np.array([[feature_distance(i, j) for j in range(n)] for i in range(n)])
-    ref = np.clip(np.sum(pair, axis=2), a_min=0, a_max=None)
+    # process_photos.py:46-56 restated with broadcasting: euclidean distance between the embeddings plus a tenth of
+    # (a_i - a_j)^2 / (a_i + a_j), a = apparent age of each face in the year of the later of the two photos; clipped at 0
+    later = np.maximum(years[:, None], years[None, :]).astype(np.float64)
+    age_i, age_j = later - born[:, None], later - born[None, :]
+    feat = np.sqrt(((f[:, None, :].astype(np.float64) - f[None, :, :].astype(np.float64)) ** 2).sum(axis=2))
+    ref = np.clip(feat + 0.1 * (age_i - age_j) ** 2 / (age_i + age_j), 0, None)
     got = hfr.album_distance_matrix(f, years, born)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
     with pytest.raises(ValueError):

@@ -1,22 +1,37 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the hot path (contract: see DESIGN.md "Measurement").
+"""bench.py - benchmark of the hot path (contract: DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mobilenet192|agegender224|resnet50|knn]
-  python bench.py --impl reference ...      # the CPU restatement of the reference's path on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # headline + every other BASELINE workload
+  python bench.py --only mobilenet192|agegender224|resnet50|knn [--precision bf16|tf32] [--layers]
+  python bench.py --impl reference ...                            # the reference's CPU path on the host cores
 
-One "step" = one pass of the hot path over one batch of synthetic input.  Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of synthetic input.  Rank 0 prints ONE JSON line.  The top level
+is the headline workload (ResNet-50, batch 256, bf16 - BASELINE.json configs[1]); `workloads` holds the same record
+(value, e2e, roofline, cpu_baseline, clocks) for the other configurations BASELINE.json's metric names:
+MobileNet-192 batch 64, the age/gender MobileNet-224 batch 256, ResNet-50 in tf32 mode and the 1-NN identification
+(100k queries x 1M x 1024 gallery, row-sharded over the N ranks, NCCL all-gather merge: the one collective of the path).
   value   whole-job throughput, inputs resident in HBM, CUDA-graph replay, CUDA-event timed, max over ranks
   e2e     the same metric through the host-buffer C-ABI call (pinned host input -> H2D -> run -> D2H of the result)
   roofline  dominant kernel class: algorithmic bytes|flops per launch / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline  oracle (torch-CPU port; sklearn for 1-NN = the reference's real dependency) on a bounded sample
+  cpu_baseline  oracle (torch-CPU port; sklearn for 1-NN = the reference's real dependency) on a bounded sample,
+          rank 0 at N=1 only
+The reference arm never imports the product package (no libhfr.so in that process).
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
+
+_NCPU = os.cpu_count() or 1
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core, set before numpy / torch / sklearn load
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(_NCPU)
+
+import argparse
+import importlib.util
+import json
+import subprocess
 import threading
 import time
 
@@ -37,15 +52,36 @@ WORKLOADS = {
     "knn": ("1-NN identification: 100k queries vs 1M x 1024 L2-normalised synthetic gallery (row-sharded over the "
             "GPUs, NCCL all-gather top-1 merge)", 100_000, 1024, "1-NN queries/sec", "queries/s"),
 }
+HEADLINE = ("resnet50", "bf16")
+OTHERS = [("mobilenet192", "bf16"), ("agegender224", "bf16"), ("resnet50", "tf32"), ("knn", "bf16")]
+
+
+def _synth():
+    """tests' fixture writer (hse_facerec_tf_b200/synth.py) loaded BY PATH: importing the package would dlopen
+    libhfr.so, which the reference arm must not do."""
+    spec = importlib.util.spec_from_file_location("_hfr_synth", os.path.join(ROOT, "hse_facerec_tf_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"],
-                "source": "measured"}
-    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+        out = {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"],
+               "source": "measured"}
+    # tf32: MEASURED_PEAKS.json has no tf32 figure; profiles/peaks_probe.json holds ours, taken with the same probe
+    q = os.path.join(ROOT, "profiles", "peaks_probe.json")
+    if os.path.exists(q):
+        d = json.load(open(q))
+        out["tensor_tf32"] = d["tf32_tflops_sustained"]
+        out["tf32_source"] = "profiles/peaks_probe.json (same probe as MEASURED_PEAKS.json, tf32 matmul)"
+    else:
+        out["tensor_tf32"] = out["tensor"] / 2
+        out["tf32_source"] = "bf16 sustained / 2 (no tf32 probe available)"
+    return out
 
 
 class ClockSampler:
@@ -82,12 +118,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------------ networks
+# ------------------------------------------------------------------------------------------------------ workloads
 def synth_images(batch, size, seed):
     return np.random.RandomState(seed).randint(0, 256, (batch, size, size, 3)).astype(np.uint8)
 
 
-def model_spec(workload, precision):
+def model_spec(workload):
     if workload == "mobilenet192":
         return dict(path=PB, input="input_1:0", outputs=["global_pooling/Mean:0"], hw=192, bgr=True, imagenet=True)
     if workload == "agegender224":
@@ -95,14 +131,33 @@ def model_spec(workload, precision):
                     outputs=["age_pred/Softmax:0", "gender_pred/Sigmoid:0", "global_pooling/Mean:0"], hw=0, bgr=True,
                     imagenet=True)
     if workload == "resnet50":
-        from hse_facerec_tf_b200.synth import ensure_resnet50_pb
-        return dict(path=ensure_resnet50_pb(), input="input:0", outputs=["pool5_7x7_s1:0"], hw=0, bgr=True,
+        return dict(path=_synth().ensure_resnet50_pb(), input="input:0", outputs=["pool5_7x7_s1:0"], hw=0, bgr=True,
                     imagenet=False)
     raise ValueError(workload)
 
 
+def input_rotation(batch, size):
+    """distinct input batches the timed loop rotates over: enough that the inputs alone exceed the 126 MB L2"""
+    in_bytes = batch * size * size * 3
+    return max(2, min(32, -(-140_000_000 // in_bytes))), in_bytes
+
+
+def workload_config(workload, world, batch=0, gallery=1_000_000):
+    """The `config` object of a workload: identical in the product arm and in the reference arm."""
+    desc, b, size, metric, unit = WORKLOADS[workload]
+    b = batch or b
+    if workload == "knn":
+        return dict(workload="knn", description=desc, queries=b, gallery=gallery, dim=size, shards=world,
+                    parallelism=f"gallery row-sharded x{world}",
+                    l2_policy=f"gallery shard {(gallery // world) * size * 2 / 1e9:.1f} GB (bf16) >> L2")
+    nrot, in_bytes = input_rotation(b, size)
+    return dict(workload=workload, description=desc, per_gpu_batch=b, global_batch=b * world,
+                input=f"{size}x{size}x3 uint8", parallelism=f"dp{world}",
+                l2_policy=f"inputs rotate over {nrot} distinct batches ({nrot * in_bytes / 1e6:.0f} MB > L2)")
+
+
 def plan_work(plan, es):
-    """Algorithmic work per image from the compiled plan: per layer (flops, bytes moved in+out+weights-once-ignored)."""
+    """Algorithmic work per image from the compiled plan: per layer (flops, bytes moved in+out; weights ignored)."""
     rows = []
     for L in plan["layers"]:
         hin, win = L["hw_in"]
@@ -113,15 +168,15 @@ def plan_work(plan, es):
             flops = 2.0 * ho * wo * L["cout"] * L["cin"] * k
         elif kind == "dw":
             flops = 2.0 * ho * wo * L["cout"] * 9
-        elif kind == "fc":
+        elif kind in ("fc", "head"):
             flops = 2.0 * L["cin"] * L["cout"]
         else:
             flops = 0.0
         in_b = hin * win * L["cin"] * (1 if kind == "stem" else es)
         if kind == "subsample":
             in_b = ho * wo * L["cin"] * es      # only every stride-th pixel is read
-        out_b = ho * wo * L["cout"] * (4 if kind in ("gap", "fc") else es)
-        if kind == "fc":
+        out_b = ho * wo * L["cout"] * (4 if kind in ("gap", "fc", "head") else es)
+        if kind in ("fc", "head"):
             in_b, out_b = L["cin"] * 4, L["cout"] * 4
         if L["in2"] >= 0:
             in_b += ho * wo * L["cout"] * es
@@ -129,31 +184,35 @@ def plan_work(plan, es):
     return rows
 
 
-def bench_network(args, rank, world, dev):
+KERNEL_NAMES = {"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)",
+                "conv": "gemm_tc_kernel (im2col) / conv_window_kernel", "dw": "dwconv3x3_pipe_kernel"}
+
+
+def bench_network(workload, precision, args, rank, world, dev):
     import torch
+    import torch.distributed as dist
     import hse_facerec_tf_b200 as hfr
-    desc, batch, size, metric, unit = WORKLOADS[args.workload]
+    desc, batch, size, metric, unit = WORKLOADS[workload]
     batch = args.batch or batch
-    spec = model_spec(args.workload, args.precision)
+    spec = model_spec(workload)
     model = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=f"cuda:{dev}",
-                         precision=args.precision)
-    es = 2 if args.precision == "bf16" else 4
+                         precision=precision)
+    es = 2 if precision == "bf16" else 4
     size = model.h
-    # rotate over enough distinct input batches that the inputs alone exceed the 126 MB L2
-    in_bytes = batch * size * size * 3
-    nrot = max(2, min(32, -(-140_000_000 // in_bytes)))
+    nrot, in_bytes = input_rotation(batch, size)
     xs = [torch.from_numpy(synth_images(batch, size, 1000 * rank + i)).to(f"cuda:{dev}") for i in range(nrot)]
     outs = [[torch.empty((batch, d), dtype=torch.float32, device=f"cuda:{dev}") for d in model.out_dims]
             for _ in range(nrot)]
     stream = torch.cuda.Stream(device=dev)
     kw = dict(convert2BGR=spec["bgr"], imageNetUtilsMean=spec["imagenet"])
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     def step(i, graph=not args.no_graph):
         model.forward(xs[i % nrot], graph=graph, outs=outs[i % nrot], **kw)
 
-    import torch.distributed as dist
+    e2e_s, host_s = None, [0.0, 0.0]
     with torch.cuda.stream(stream):
-        for i in range(max(args.warmup, 3) + nrot):          # warm-up (also captures one graph per input buffer)
+        for i in range(warmup + nrot):          # warm-up (also captures one graph per input buffer)
             step(i)
         stream.synchronize()
         launches0 = hfr.launch_count()
@@ -177,7 +236,7 @@ def bench_network(args, rank, world, dev):
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.steps):
+        for i in range(steps):
             step(i)
         e1.record(stream)
         stream.synchronize()
@@ -187,80 +246,81 @@ def bench_network(args, rank, world, dev):
         torch.cuda.synchronize(dev)
         clocks = sampler.stop()
 
-        # ---- e2e: pinned host batch -> H2D -> run -> D2H of the result, through the host-buffer C-ABI call
-        # The streaming form of the call (hfr_model_submit_host / hfr_model_wait_host, two batches in flight): every
-        # step's input still travels pinned host -> device and its result device -> pinned host inside the timed region,
-        # but step i+1's upload and step i-1's download overlap step i's compute.
-        depth = int(os.environ.get("HFR_BENCH_E2E_DEPTH", "2"))
-        hx = [torch.from_numpy(synth_images(batch, size, 5000 + 1000 * rank + i)).pin_memory() for i in range(depth)]
-        houts = [[torch.empty((batch, d), dtype=torch.float32).pin_memory().numpy() for d in model.out_dims]
-                 for _ in range(depth)]
+        if not args.no_e2e:
+            # ---- e2e: pinned host batch -> H2D -> run -> D2H of the result, through the host-buffer C-ABI call.
+            # Streaming form (hfr_model_submit_host / hfr_model_wait_host, `depth` batches in flight): every step's
+            # input still travels pinned host -> device and its result device -> pinned host inside the timed region,
+            # but step i+1's upload and step i-1's download overlap step i's compute.
+            depth = int(os.environ.get("HFR_BENCH_E2E_DEPTH", "2"))
+            hx = [torch.from_numpy(synth_images(batch, size, 5000 + 1000 * rank + i)).pin_memory() for i in range(depth)]
+            houts = [[torch.empty((batch, d), dtype=torch.float32).pin_memory().numpy() for d in model.out_dims]
+                     for _ in range(depth)]
+            hxn = [h.numpy() for h in hx]
 
-        hxn = [h.numpy() for h in hx]
-        host_s = [0.0, 0.0]  # seconds the host spent inside submit / wait (reported on stderr)
+            def e2e_run(n):
+                for i in range(n):
+                    ta = time.perf_counter()
+                    if i >= depth:
+                        model.wait_host(i % depth)
+                    tb = time.perf_counter()
+                    model.submit_host(i % depth, hxn[i % depth], houts[i % depth], graph=True, **kw)
+                    host_s[0] += time.perf_counter() - tb
+                    host_s[1] += tb - ta
+                for sl in range(depth):
+                    model.wait_host(sl)
 
-        def e2e_run(n):
-            for i in range(n):
-                ta = time.perf_counter()
-                if i >= depth:
-                    model.wait_host(i % depth)
-                tb = time.perf_counter()
-                model.submit_host(i % depth, hxn[i % depth], houts[i % depth], graph=True, **kw)
-                host_s[0] += time.perf_counter() - tb
-                host_s[1] += tb - ta
-            for sl in range(depth):
-                model.wait_host(sl)
-
-        e2e_run(4)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        host_s[0] = host_s[1] = 0.0
-        e2e_run(args.steps)
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        print(f"[e2e] depth {depth}: {e2e_s / args.steps * 1e3:.3f} ms/step; host in submit {host_s[0] / args.steps * 1e3:.3f} ms, "
-              f"in wait {host_s[1] / args.steps * 1e3:.3f} ms per step", file=sys.stderr)
+            e2e_run(4)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            host_s[0] = host_s[1] = 0.0
+            e2e_run(steps)
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t0
 
         # ---- per-kernel durations (CUDA events around every layer launch, eager, same stream)
         model.layer_timing(True)
-        for i in range(min(args.steps, 20)):
+        for i in range(min(steps, 20)):
             step(i, graph=False)
         lms, lsteps = model.layer_times()
         model.layer_timing(False)
 
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device=f"cuda:{dev}", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s or 0.0], device=f"cuda:{dev}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s = float(t[0]), (float(t[1]) if e2e_s is not None else None)
+    plan = model.plan()
+    out_dims = list(model.out_dims)
+    model.close()
+    del xs, outs
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
 
     pk = peaks()
-    work = plan_work(model.plan(), es)
+    tensor_peak = pk["tensor"] if precision == "bf16" else pk["tensor_tf32"]
+    work = plan_work(plan, es)
     classes = {}
-    # a depthwise layer followed by a pointwise layer with an empty interval ran as ONE fused dwpw_kernel launch:
-    # book the pair as class "dwpw" (flops of both, bytes = depthwise input + pointwise output)
     per_step = [t / max(lsteps, 1) for t in lms]
     merged = []
     i = 0
     while i < len(work):
         w, t = dict(work[i]), per_step[i]
+        # a depthwise layer followed by a pointwise layer with an empty interval ran as ONE fused dwpw_kernel launch
         if w["kind"] == "dw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 2e-4:
-            L0, L1 = model.plan()["layers"][i], model.plan()["layers"][i + 1]
+            L0, L1 = plan["layers"][i], plan["layers"][i + 1]
             w = dict(kind="dwpw", name=work[i + 1]["name"], flops=work[i]["flops"] + work[i + 1]["flops"],
                      bytes=float((L0["hw_in"][0] * L0["hw_in"][1] * L0["cin"] + L1["hw_out"][0] * L1["hw_out"][1] * L1["cout"]) * es))
             i += 1
-        if w["kind"] == "subsample" and t < 5e-3:
-            i += 1      # bypassed: its consumers fetch the strided pixels themselves (im2col map), nothing was launched
+        if t < 5e-4 and w["kind"] in ("subsample", "maxpool", "gap", "fc"):
+            i += 1      # nothing launched: bypassed gather, or a layer fused into its neighbour's kernel
             continue
         merged.append((w, t))
         i += 1
     for w, t in merged:
-        t = t * max(lsteps, 1)
         c = classes.setdefault(w["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-        c["ms"] += t / max(lsteps, 1)
+        c["ms"] += t
         c["flops"] += w["flops"] * batch
         c["bytes"] += w["bytes"] * batch
         c["launches"] += 1
@@ -268,11 +328,11 @@ def bench_network(args, rank, world, dev):
     for kname, c in classes.items():
         if c["ms"] <= 0:
             continue
-        # each class is compared with BOTH roofs (algorithmic flops vs measured bf16 peak, algorithmic bytes vs measured
-        # HBM copy bandwidth); the binding roof is the one it sits closer to
+        # each class is compared with BOTH roofs (algorithmic flops vs measured tensor peak of this precision,
+        # algorithmic bytes vs measured HBM copy bandwidth); the binding roof is the one it sits closer to
         tf = c["flops"] / (c["ms"] * 1e-3) / 1e12
         gb = c["bytes"] / (c["ms"] * 1e-3) / 1e9
-        frac_t, frac_h = tf / pk["tensor"], gb / pk["hbm"]
+        frac_t, frac_h = tf / tensor_peak, gb / pk["hbm"]
         tensor_bound = kname in ("pw", "conv", "dwpw") and frac_t >= frac_h
         kernels[kname] = dict(ms_per_step=round(c["ms"], 5), launches=c["launches"],
                               bound="tensor" if tensor_bound else "hbm",
@@ -282,36 +342,40 @@ def bench_network(args, rank, world, dev):
                               tflops=round(tf, 2), hbm_gbs=round(gb, 1))
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     kd = kernels[dom]
-    roof = dict(kernel={"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)", "conv": "gemm_tc_kernel (im2col) / conv_window_kernel", "dw": "dwconv3x3_pipe_kernel",
-                        "stem": "stem_s2d_kernel + conv_window_kernel" if args.precision == "bf16" else "stem_conv_kernel"}.get(dom, dom),
-                bound=kd["bound"], achieved=kd["achieved"], peak=pk["tensor"] if kd["bound"] == "tensor" else pk["hbm"],
-                unit=kd["unit"], frac=kd["frac"], traffic=None, peak_source=pk["source"] + " (sustained)",
-                per_launch_ms=round(kd["ms_per_step"] / kd["launches"], 5))
+    stem_name = "stem_s2d_kernel + conv_window_kernel" if precision == "bf16" else "stem_conv_kernel"
+    roof = dict(kernel=KERNEL_NAMES.get(dom, stem_name if dom == "stem" else dom),
+                bound=kd["bound"], achieved=kd["achieved"], peak=tensor_peak if kd["bound"] == "tensor" else pk["hbm"],
+                unit=kd["unit"], frac=kd["frac"], traffic=None,
+                peak_source=(pk["source"] + " (sustained)") if (kd["bound"] == "hbm" or precision == "bf16") else pk["tf32_source"],
+                per_launch_ms=round(kd["ms_per_step"] / kd["launches"], 5),
+                algorithmic_bytes_per_launch=round(classes[dom]["bytes"] / classes[dom]["launches"]),
+                note="class times are eager CUDA-event pairs around each launch; `value` is CUDA-graph replay with "
+                     "programmatic dependent launch, so the class times sum to slightly more than ms_per_step")
     # DRAM traffic per launch of the dominant class, from the committed ncu launch list of this workload (if present)
-    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(tpath):
+    tag = workload if precision == "bf16" else f"{workload}_{precision}"
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{tag}.json")
+    if os.path.exists(tpath) and batch == WORKLOADS[workload][1]:
         tr = json.load(open(tpath)).get("classes", {}).get(dom)
-        if tr and batch == WORKLOADS[args.workload][1] and args.precision == "bf16":
+        if tr:
             roof["traffic"] = tr["dram_bytes_per_launch"]
-            roof["traffic_source"] = f"profiles/traffic_{args.workload}.json (ncu, share of step {tr['share']})"
-            roof["algorithmic_bytes_per_launch"] = round(classes[dom]["bytes"] / classes[dom]["launches"])
-    total = batch * world * args.steps
-    value = total / (ms * 1e-3)
-    out_bytes = sum(model.out_dims) * 4 * batch
-    return dict(metric=metric, value=round(value, 1), unit=unit, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype=args.precision, data="synthetic",
-                config=dict(workload=args.workload, description=desc, per_gpu_batch=batch, global_batch=batch * world,
-                            input=f"{size}x{size}x3 uint8", parallelism=f"dp{world}",
-                            l2_policy=f"inputs rotate over {nrot} distinct batches ({nrot * in_bytes / 1e6:.0f} MB > L2); "
-                                      "activations (>= 0.4 GB/step written) exceed L2",
-                            cuda_graph=not args.no_graph),
-                e2e=dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
-                         d2h_bytes_per_step=out_bytes),
-                gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step),
-                clocks=clocks, roofline=roof, kernels=kernels,
-                **({"layers": [dict(kind=w["kind"], name=w["name"], us=round(t * 1e3, 2), gflop=round(w["flops"] * batch / 1e9, 2),
-                                    mb=round(w["bytes"] * batch / 1e6, 1)) for w, t in merged]} if args.layers else {}))
+            roof["traffic_source"] = f"profiles/traffic_{tag}.json (ncu, share of step {tr['share']})"
+    total = batch * world * steps
+    rec = dict(metric=metric, value=round(total / (ms * 1e-3), 1), unit=unit, n_gpus=world, steps=steps, warmup=warmup,
+               ms_per_step=round(ms / steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype=precision, data="synthetic", config=workload_config(workload, world, batch), cuda_graph=not args.no_graph)
+    if e2e_s is not None:
+        rec["e2e"] = dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
+                          d2h_bytes_per_step=sum(out_dims) * 4 * batch,
+                          note=f"hfr_model_submit_host/wait_host, {os.environ.get('HFR_BENCH_E2E_DEPTH', '2')} batches in "
+                               f"flight; host in submit {host_s[0] / steps * 1e3:.3f} ms, in wait {host_s[1] / steps * 1e3:.3f} "
+                               "ms per step. e2e can exceed `value`: the device-resident loop draws more power and sits "
+                               "lower under the board's power cap")
+    rec.update(gpu_launches=int(launches_per_step * steps), launches_per_step=int(launches_per_step), clocks=clocks,
+               roofline=roof, kernels=kernels)
+    if args.layers:
+        rec["layers"] = [dict(kind=w["kind"], name=w["name"], us=round(t * 1e3, 2), gflop=round(w["flops"] * batch / 1e9, 2),
+                              mb=round(w["bytes"] * batch / 1e6, 1)) for w, t in merged]
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------------ 1-NN
@@ -332,26 +396,28 @@ def knn_data(n, nq, d, rank, world):
     return gal.contiguous(), q.contiguous()
 
 
-def bench_knn(args, rank, world, dev):
+def bench_knn(precision, args, rank, world, dev):
     import torch
     import torch.distributed as dist
     import hse_facerec_tf_b200 as hfr
+    from hse_facerec_tf_b200.parallel import shard_rows
     desc, nq, d, metric, unit = WORKLOADS["knn"]
     n = args.gallery
     nq = args.batch or nq
+    steps, warmup = args.steps, max(args.warmup, 3)
     gal, q = knn_data(n, nq, d, rank, world)
     if world > 1:
-        dist.broadcast_object_list([None], src=0)  # cheap sync before big allocations
         qt = q.cuda(dev)
         dist.broadcast(qt, src=0)                  # rank 0's queries (with planted neighbours) everywhere
         q = qt.cpu()
-    clf = hfr.KNeighborsClassifier(1, 2, device=f"cuda:{dev}", precision=args.precision, sharded=world > 1)
+        del qt
+    clf = hfr.KNeighborsClassifier(1, 2, device=f"cuda:{dev}", precision=precision, sharded=world > 1)
     y_local = np.arange(rank * (n // world), (rank + 1) * (n // world)) % 10000
     clf.fit(gal.cuda(dev), y_local)
     qd = q.cuda(dev)
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             clf.kneighbors(qd, return_distance=False)
         l0 = hfr.launch_count()
         clf.kneighbors(qd, return_distance=False)
@@ -361,116 +427,173 @@ def bench_knn(args, rank, world, dev):
         torch.cuda.synchronize(dev)
         sampler = ClockSampler(dev)
         sampler.start()
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < 0.5:     # untimed pre-roll: the clock sampler sees the GPU under this load
+            clf.kneighbors(qd, return_distance=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
-            clf.kneighbors(qd, return_distance=False)   # includes the D2H of the 100k indices (0.8 MB)
+        for _ in range(steps):
+            clf.kneighbors(qd, return_distance=False)   # includes the merge collective and the D2H of the indices
         e1.record(stream)
         stream.synchronize()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        # e2e: pinned host queries in, indices out
-        hq = q.pin_memory()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ind = clf.kneighbors(hq.numpy(), return_distance=False)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop()
+        e2e_s = None
+        if not args.no_e2e:
+            # e2e: pinned host queries in, indices out.  Sharded: every rank uploads ITS 1/N of the queries (the rows
+            # it would have extracted itself) and the query block is all-gathered over NVLink
+            a, b = shard_rows(nq, world, rank)
+            hq = q[a:b].contiguous().pin_memory().numpy()
+            clf.kneighbors(hq, return_distance=False, local_queries=world > 1)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                ind = clf.kneighbors(hq, return_distance=False, local_queries=world > 1)
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t0
+        else:
+            ind = clf.kneighbors(qd, return_distance=False)
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device=f"cuda:{dev}", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s or 0.0], device=f"cuda:{dev}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s = float(t[0]), (float(t[1]) if e2e_s is not None else None)
+    del clf, qd, gal
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
     m = min(nq, n // world)
     planted_ok = float((ind[:m, 0] == np.arange(m)).mean())
     pk = peaks()
+    tensor_peak = pk["tensor"] if precision == "bf16" else pk["tensor_tf32"]
     flops = 2.0 * nq * (n // world) * d
-    per_step_ms = ms / args.steps
+    per_step_ms = ms / steps
     ach = flops / (per_step_ms * 1e-3) / 1e12
-    return dict(metric=metric, value=round(nq * args.steps / (ms * 1e-3), 1), unit=unit, n_gpus=world, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=round(per_step_ms, 3), higher_is_better=True, scaling="strong",
-                vs_baseline=None, dtype=args.precision, data="synthetic",
-                config=dict(workload="knn", description=desc, queries=nq, gallery=n, dim=d, shards=world,
-                            parallelism=f"gallery row-sharded x{world}",
-                            l2_policy=f"gallery shard {(n // world) * d * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB >> L2",
-                            planted_neighbour_recall=planted_ok),
-                e2e=dict(value=round(nq * args.steps / e2e_s, 1), unit=unit, h2d_bytes_per_step=nq * d * 4,
-                         d2h_bytes_per_step=nq * 8),
-                gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step), clocks=clocks,
-                roofline=dict(kernel="gemm_tc_kernel (EPI_KNN) incl. prep+finalize in the step time", bound="tensor",
-                              achieved=round(ach, 2), peak=pk["tensor"], unit="TFLOP/s", frac=round(ach / pk["tensor"], 4),
-                              traffic=None, peak_source=pk["source"] + " (sustained)"))
+    cfg = workload_config("knn", world, nq, n)
+    cfg["planted_neighbour_recall"] = planted_ok
+    rec = dict(metric=metric, value=round(nq * steps / (ms * 1e-3), 1), unit=unit, n_gpus=world, steps=steps,
+               warmup=warmup, ms_per_step=round(per_step_ms, 3), higher_is_better=True, scaling="strong",
+               vs_baseline=None, dtype=precision, data="synthetic", config=cfg)
+    if e2e_s is not None:
+        rec["e2e"] = dict(value=round(nq * steps / e2e_s, 1), unit=unit, h2d_bytes_per_step=(b - a) * d * 4,
+                          d2h_bytes_per_step=nq * 8,
+                          note="per rank: its 1/N block of the queries pinned host -> device, all-gathered over NVLink; "
+                               "all indices back to the host")
+    tpath = os.path.join(ROOT, "profiles", "traffic_knn.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) and world == 1 and nq == 100_000 and n == 1_000_000 else None
+    rec.update(gpu_launches=int(launches_per_step * steps), launches_per_step=int(launches_per_step), clocks=clocks,
+               roofline=dict(kernel="gemm_tc_kernel<EPI_KNN> (step time also holds rows_prep + finalize + merge)",
+                             bound="tensor", achieved=round(ach, 2), peak=tensor_peak, unit="TFLOP/s",
+                             frac=round(ach / tensor_peak, 4),
+                             traffic=traffic["dram_bytes_per_launch"] if traffic else None,
+                             **({"traffic_source": traffic["source"]} if traffic else {}),
+                             algorithmic_flops_per_launch=flops,
+                             peak_source=(pk["source"] + " (sustained)") if precision == "bf16" else pk["tf32_source"]))
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------------ CPU legs
-def cpu_network(args, budget_s=12.0):
-    """Oracle port (torch-CPU restatement of the frozen graph) on all host cores; bounded sample."""
+def cpu_network(workload, steps, warmup, batch=0, budget_s=None):
+    """Oracle port (torch-CPU restatement of the frozen graph) on all host cores.  steps x the workload's batch (a
+    bounded sample when budget_s cuts it short); returns (cpu_baseline dict, steps done, seconds per step)."""
     import torch
     from oracle.tfnet import GraphOracle, preprocess_rgb_u8
-    desc, batch, size, metric, unit = WORKLOADS[args.workload]
-    spec = model_spec(args.workload, "tf32")
-    torch.set_num_threads(os.cpu_count())
+    desc, b, size, metric, unit = WORKLOADS[workload]
+    b = batch or b
+    spec = model_spec(workload)
+    torch.set_num_threads(_NCPU)
     g = GraphOracle(spec["path"])
     size = spec["hw"] or (g.placeholder_shape(spec["input"]) or [0, 224])[1]
-    sample = min(args.batch or batch, 16)
-    x = preprocess_rgb_u8(synth_images(sample, size, 0), True, spec["imagenet"])
-    g.run([o for o in spec["outputs"]], {spec["input"]: x})      # warm-up
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
-        g.run([o for o in spec["outputs"]], {spec["input"]: x})
-        n += sample
+    nrot = min(input_rotation(b, size)[0], 4)
+    xs = [preprocess_rgb_u8(synth_images(b, size, i), True, spec["imagenet"]) for i in range(nrot)]
+    for i in range(warmup):
+        g.run(list(spec["outputs"]), {spec["input"]: xs[i % nrot]})
+    done, t0 = 0, time.perf_counter()
+    for i in range(steps):
+        g.run(list(spec["outputs"]), {spec["input"]: xs[i % nrot]})
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return dict(value=round(n / dt, 2), unit=unit, cores=torch.get_num_threads(), kind="port",
-                sample=f"{n} images in batches of {sample} at {size}x{size} through oracle/tfnet.py (torch-CPU fp32, "
-                       f"{dt:.1f} s); TensorFlow itself is not installable here")
+    cb = dict(value=round(done * b / dt, 2), unit=unit, cores=torch.get_num_threads(), kind="port",
+              sample=f"{done} batches of {b} images at {size}x{size} through oracle/tfnet.py (torch-CPU fp32, {dt:.1f} s); "
+                     "TensorFlow itself is not installable here")
+    return cb, done, dt / max(done, 1)
 
 
-def cpu_knn(args, budget_q=1500):
-    """The reference's real dependency: sklearn KNeighborsClassifier(n_neighbors=1, p=2).kneighbors; query subsample."""
+def cpu_knn(gallery, steps, warmup, queries_per_step=300):
+    """The reference's real dependency: sklearn KNeighborsClassifier(n_neighbors=1, p=2).kneighbors on a query subsample
+    against the full gallery."""
     from sklearn import neighbors
     desc, nq, d, metric, unit = WORKLOADS["knn"]
-    n = min(args.gallery, 1_000_000)
-    gal, q = knn_data(n, budget_q, d, 0, 1)
+    n = min(gallery, 1_000_000)
+    gal, q = knn_data(n, queries_per_step * max(steps, 1), d, 0, 1)
     nn = neighbors.KNeighborsClassifier(n_neighbors=1, p=2).fit(gal.numpy(), np.arange(n) % 10000)
+    qn = q.numpy()
+    for _ in range(warmup):
+        nn.kneighbors(qn[:32], return_distance=False)
     t0 = time.perf_counter()
-    nn.kneighbors(q.numpy(), return_distance=False)
+    for i in range(steps):
+        nn.kneighbors(qn[i * queries_per_step:(i + 1) * queries_per_step], return_distance=False)
     dt = time.perf_counter() - t0
-    return dict(value=round(budget_q / dt, 2), unit=unit, cores=os.cpu_count(), kind="reference",
-                sample=f"scikit-learn kneighbors on {budget_q} of the {nq} queries vs the full {n} x {d} gallery ({dt:.1f} s), "
-                       "extrapolated linearly")
+    cb = dict(value=round(queries_per_step * steps / dt, 2), unit=unit, cores=_NCPU, kind="reference",
+              sample=f"scikit-learn kneighbors: {steps} steps of {queries_per_step} of the {nq} queries vs the full {n} x {d} "
+                     f"gallery ({dt:.1f} s), extrapolated linearly")
+    return cb, steps, dt / max(steps, 1)
+
+
+def reference_record(workload, args, steps, warmup):
+    desc, batch, size, metric, unit = WORKLOADS[workload]
+    if workload == "knn":
+        cb, done, s_per = cpu_knn(args.gallery, steps, min(warmup, 1))
+        ms_per_step = batch / cb["value"] * 1e3      # time this arm needs for one step of the product arm's size
+    else:
+        cb, done, s_per = cpu_network(workload, steps, warmup, args.batch)
+        ms_per_step = s_per * 1e3
+    v = cb["value"]
+    return dict(impl="reference", metric=metric, value=v, unit=unit, n_gpus=args.gpus, steps=done, warmup=warmup,
+                ms_per_step=round(ms_per_step, 1), higher_is_better=True,
+                scaling="strong" if workload == "knn" else "weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config(workload, args.gpus, args.batch, args.gallery), cpu_baseline=cb,
+                e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on this box's host cores, same config/metric/unit."""
-    desc, batch, size, metric, unit = WORKLOADS[args.workload]
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        cb = cpu_knn(args, 600) if args.workload == "knn" else cpu_network(args, 6.0)
-        vals.append(cb["value"])
-    v = float(np.mean(vals))
-    cb["value"] = v
-    print(json.dumps(dict(impl="reference", metric=metric, value=round(v, 2), unit=unit, n_gpus=args.gpus,
-                          steps=len(vals), warmup=1,
-                          # time this arm needs for one step of the GPU arm's size (batch images / nq queries),
-                          # extrapolated from the bounded samples
-                          ms_per_step=round(batch / v * 1e3, 1), higher_is_better=True,
-                          scaling="strong" if args.workload == "knn" else "weak", vs_baseline=None, dtype="f32",
-                          data="synthetic", config=dict(workload=args.workload, description=desc), cpu_baseline=cb,
-                          e2e=dict(value=round(v, 2), unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+    """--impl reference: the CPU implementation of the path on this box's host cores; same config / metric / unit /
+    steps as the product arm.  The headline runs the full K steps + W warm-ups of the full batch; the other workloads
+    run a few steps each so that the whole arm ends within a few minutes."""
+    if args.only:
+        print(json.dumps(reference_record(args.only, args, args.steps, args.warmup)))
+        return
+    rec = reference_record(HEADLINE[0], args, args.steps, args.warmup)
+    rec["workloads"] = {}
+    for w, prec in OTHERS:
+        if prec != "bf16" and w == HEADLINE[0]:
+            continue        # the CPU arm has one precision (fp32): resnet50_tf32 compares with the headline record
+        rec["workloads"][w] = reference_record(w, args, min(args.steps, 5), 1)
+    print(json.dumps(rec))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="hfr", choices=["hfr", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("HFR_BENCH_WORKLOAD", "resnet50"), choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--only", "--workload", dest="only", default=os.environ.get("HFR_BENCH_WORKLOAD"),
+                    choices=list(WORKLOADS), help="run one workload only (default: headline + all the others)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"], help="with --only")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (queries for knn)")
     ap.add_argument("--gallery", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (ncu captures)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--layers", action="store_true", help="add per-layer event timings to the JSON line")
     args = ap.parse_args()
@@ -481,8 +604,6 @@ def main():
         if rank == 0:
             run_reference(args)
         return
-    if args.workload == "knn" and args.steps > 10:
-        args.steps = 5
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
@@ -490,10 +611,35 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    res = bench_knn(args, rank, world, local) if args.workload == "knn" else bench_network(args, rank, world, local)
+
+    def one(workload, precision, cpu=True):
+        t0 = time.perf_counter()
+        rec = (bench_knn(precision, args, rank, world, local) if workload == "knn"
+               else bench_network(workload, precision, args, rank, world, local))
+        if rank == 0:
+            if world == 1 and cpu and not args.no_cpu_baseline:     # rank 0 at N=1 only
+                if workload == "knn":
+                    rec["cpu_baseline"] = cpu_knn(args.gallery, 5, 1)[0]
+                else:
+                    rec["cpu_baseline"] = cpu_network(workload, 1000, 1, args.batch, budget_s=10.0)[0]
+            print(f"[bench] {workload} {precision}: {rec['value']} {rec['unit']} ({time.perf_counter() - t0:.1f} s)",
+                  file=sys.stderr)
+        return rec
+
+    if args.only:
+        res = one(args.only, args.precision)
+    else:
+        res = one(*HEADLINE)
+        others = {}
+        for w, prec in OTHERS:
+            r = one(w, prec, cpu=not (w == HEADLINE[0]))
+            if rank == 0:
+                if w == HEADLINE[0] and "cpu_baseline" in res:
+                    r["cpu_baseline"] = res["cpu_baseline"]      # same CPU path (fp32), not timed twice
+                others[w if prec == "bf16" else f"{w}_{prec}"] = r
+        if rank == 0:
+            res["workloads"] = others
     if rank == 0:
-        if not args.no_cpu_baseline:
-            res["cpu_baseline"] = cpu_knn(args) if args.workload == "knn" else cpu_network(args)
         print(json.dumps(res))
     if world > 1:
         import torch.distributed as dist

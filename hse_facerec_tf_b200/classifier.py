@@ -97,7 +97,10 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         check(lib.hfr_knn_set_gallery(h, g.data_ptr(), g.shape[0], offset, _stream_ptr(g.device)))
         return self
 
-    def kneighbors(self, X, n_neighbors=None, return_distance=True):
+    def kneighbors(self, X, n_neighbors=None, return_distance=True, local_queries=False):
+        """sklearn's kneighbors.  local_queries=True (sharded gallery only): X holds THIS rank's block of the queries
+        (contiguous blocks in rank order, e.g. the embeddings it extracted from its slice of the batch); the blocks
+        are all-gathered over NCCL and every rank returns the neighbours of the whole query set."""
         if getattr(self, "_knn", None) is None:
             from sklearn.exceptions import NotFittedError
             raise NotFittedError("This KNeighborsClassifier instance is not fitted yet.")
@@ -113,6 +116,9 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
                              f"{self.n_features_in_} features as input")
         if self._pad:
             q = torch.nn.functional.pad(q, (0, self._pad))
+        if local_queries and self.sharded:
+            from .parallel import gather_rows
+            q = gather_rows(q, self.process_group)
         nq = q.shape[0]
         if nq == 0:
             empty = np.zeros((0, k), np.int64)

@@ -426,11 +426,19 @@ struct hfr_model {
 
   void* val_ptr(int v, int batch) const { return (char*)arena.p + val_off[(size_t)v] * (size_t)batch; }
 
+  // Every cached graph bakes device pointers (arena, stem staging buffer) into its kernel arguments: whenever one of
+  // those buffers is reallocated the cache goes, after everything that may still be replaying it has drained.
+  void drop_graphs() {
+    if (graphs.empty()) return;
+    cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+  }
+
   void ensure_arena(int batch) {
     const size_t need = per_image_bytes * (size_t)batch;
     if (need > arena.bytes) {
-      for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-      graphs.clear();
+      drop_graphs();
       arena.ensure(need);
     }
   }
@@ -545,7 +553,9 @@ struct hfr_model {
           }
           const size_t need = (size_t)batch * (L.Ho + g.ka - 1) * (L.Wo + g.kb - 1) * 32;
           if (need > stem_scratch.bytes) {
+            // never reached under stream capture: forward() runs every new (batch, flags) eagerly once before capturing
             cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // previous users of the old buffer
+            drop_graphs();  // graphs captured at smaller batches hold the old pointer
             stem_scratch.ensure(need);
           }
           t.scratch = stem_scratch.p;
@@ -664,12 +674,7 @@ struct hfr_model {
     GraphKey key{x, in_dtype, batch, flags, std::vector<void*>(outs, outs + plan.outputs.size())};
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-      if (graphs.size() >= 64) {
-        // batches submitted through hfr_model_submit_host may still be replaying some of these graphs
-        cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
-        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-        graphs.clear();
-      }
+      if (graphs.size() >= 64) drop_graphs();  // (batches submitted through hfr_model_submit_host may still replay them)
       run_layers(x, in_dtype, batch, flags, outs, s);  // eager first pass: configures kernels, validates arguments
       cudaGraph_t g = nullptr;
       cuda_check(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
@@ -876,9 +881,8 @@ int hfr_model_set_keep_activations(hfr_model* m, int keep) {
   return guarded([&] {
     if (!m) throw Error(HFR_ERR_INVALID, "null model");
     m->keep_all = keep != 0;
+    m->drop_graphs();
     m->plan_arena();
-    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
-    m->graphs.clear();
   });
 }
 

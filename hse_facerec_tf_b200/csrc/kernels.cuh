@@ -3,6 +3,7 @@
 // All activations are NHWC.  T is the activation storage type: __nv_bfloat16 (bf16 mode) or float (tf32 / fp32 modes).
 #pragma once
 #include "gemm_tc.cuh"
+#include "knn.cuh"
 
 namespace hfr {
 
@@ -945,199 +946,6 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// 1-NN helpers.
-// rows fp32 -> bf16 copy (optional) + squared L2 norms in fp32.  Warp per row.
-__global__ void rows_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ nrm,
-                                 long long n, int d) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* xr = x + row * d;
-  float s = 0.f;
-  for (int j = lane * 4; j < d; j += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + j);
-    s = fmaf(v.x, v.x, s);
-    s = fmaf(v.y, v.y, s);
-    s = fmaf(v.z, v.z, s);
-    s = fmaf(v.w, v.w, s);
-    if (xb) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-      *reinterpret_cast<uint2*>(xb + row * d + j) = o;
-    }
-  }
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0 && nrm) nrm[row] = s;
-}
-
-// Final selection: per query, merge the per-split top-2 candidates, keep the KEEP best approximate scores, then re-rank
-// those exactly - squared euclidean distance accumulated in fp64 from the fp32 originals (sklearn computes in fp64:
-// _argkmin.pyx / _middle_term_computer.pyx) - ties to the lowest gallery index.  Warp per query.
-template <int KEEP>
-__global__ void knn_finalize_kernel(const float* __restrict__ q, const float* __restrict__ g,
-                                    const float* __restrict__ part_score, const int* __restrict__ part_idx, int splits,
-                                    long long nq, int d, long long row_offset, float* __restrict__ best_dist,
-                                    long long* __restrict__ best_idx) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= nq) return;
-  const int ncand = splits * 4;  // per split: 2 epilogue warpgroups x top-2
-  // each lane keeps its own KEEP best, then the warp extracts the global KEEP best one at a time
-  float ls[KEEP];
-  int li[KEEP];
-#pragma unroll
-  for (int k = 0; k < KEEP; ++k) {
-    ls[k] = INFINITY;
-    li[k] = -1;
-  }
-  for (int j = lane; j < ncand; j += 32) {
-    float s = part_score[row * ncand + j];
-    int i = part_idx[row * ncand + j];
-    if (i < 0) continue;
-#pragma unroll
-    for (int k = 0; k < KEEP; ++k) {
-      if (s < ls[k] || (s == ls[k] && i < li[k])) {
-        const float ts = ls[k];
-        const int ti = li[k];
-        ls[k] = s;
-        li[k] = i;
-        s = ts;
-        i = ti;
-      }
-    }
-  }
-  double bd = INFINITY;
-  int bi = -1;
-  for (int k = 0; k < KEEP; ++k) {
-    // warp-wide minimum of the lanes' current heads
-    float hs = ls[0];
-    int hi = li[0];
-    for (int o = 16; o; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, hs, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, hi, o);
-      if (oi >= 0 && (hi < 0 || os < hs || (os == hs && oi < hi))) {
-        hs = os;
-        hi = oi;
-      }
-    }
-    if (hi < 0) break;
-    if (li[0] == hi) {  // pop it from the owning lane
-#pragma unroll
-      for (int t = 0; t + 1 < KEEP; ++t) {
-        ls[t] = ls[t + 1];
-        li[t] = li[t + 1];
-      }
-      ls[KEEP - 1] = INFINITY;
-      li[KEEP - 1] = -1;
-    }
-    const float* qr = q + row * d;
-    const float* gr = g + (long long)hi * d;
-    double acc = 0.0;
-    for (int j = lane; j < d; j += 32) {
-      const double df = (double)qr[j] - (double)gr[j];
-      acc = fma(df, df, acc);
-    }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (acc < bd || (acc == bd && hi < bi)) {
-      bd = acc;
-      bi = hi;
-    }
-  }
-  if (lane == 0) {
-    best_dist[row] = (float)bd;
-    best_idx[row] = bi < 0 ? -1 : row_offset + bi;
-  }
-}
-
-// k-NN variant (k <= 4): ncand = splits * 2 warpgroups * 4 candidates per query; the KEEP best approximate scores are
-// re-ranked exactly (fp64, as above) and the k nearest written in ascending (distance, index) order - the order
-// sklearn's kneighbors returns; missing neighbours (gallery smaller than k) are (inf, -1).
-template <int KEEP>
-__global__ void knn_finalize_k_kernel(const float* __restrict__ q, const float* __restrict__ g,
-                                      const float* __restrict__ part_score, const int* __restrict__ part_idx, int ncand,
-                                      long long nq, int d, long long row_offset, int k, float* __restrict__ out_dist,
-                                      long long* __restrict__ out_idx) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= nq) return;
-  float ls[KEEP];
-  int li[KEEP];
-#pragma unroll
-  for (int t = 0; t < KEEP; ++t) {
-    ls[t] = INFINITY;
-    li[t] = -1;
-  }
-  for (int j = lane; j < ncand; j += 32) {
-    float s = part_score[row * ncand + j];
-    int i = part_idx[row * ncand + j];
-    if (i < 0) continue;
-#pragma unroll
-    for (int t = 0; t < KEEP; ++t) {
-      if (s < ls[t] || (s == ls[t] && i < li[t])) {
-        const float ts = ls[t];
-        const int ti = li[t];
-        ls[t] = s;
-        li[t] = i;
-        s = ts;
-        i = ti;
-      }
-    }
-  }
-  double bd[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-  int bi[4] = {-1, -1, -1, -1};
-  for (int c = 0; c < KEEP; ++c) {
-    float hs = ls[0];
-    int hi = li[0];
-    for (int o = 16; o; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, hs, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, hi, o);
-      if (oi >= 0 && (hi < 0 || os < hs || (os == hs && oi < hi))) {
-        hs = os;
-        hi = oi;
-      }
-    }
-    if (hi < 0) break;
-    if (li[0] == hi) {
-#pragma unroll
-      for (int t = 0; t + 1 < KEEP; ++t) {
-        ls[t] = ls[t + 1];
-        li[t] = li[t + 1];
-      }
-      ls[KEEP - 1] = INFINITY;
-      li[KEEP - 1] = -1;
-    }
-    const float* qr = q + row * d;
-    const float* gr = g + (long long)hi * d;
-    double acc = 0.0;
-    for (int j = lane; j < d; j += 32) {
-      const double df = (double)qr[j] - (double)gr[j];
-      acc = fma(df, df, acc);
-    }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    // sorted insert into the exact top-4 (ascending distance, ties to the lowest index)
-    double cd = acc;
-    int ci = hi;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (ci >= 0 && (bi[t] < 0 || cd < bd[t] || (cd == bd[t] && ci < bi[t]))) {
-        const double td = bd[t];
-        const int ti = bi[t];
-        bd[t] = cd;
-        bi[t] = ci;
-        cd = td;
-        ci = ti;
-      }
-    }
-  }
-  if (lane == 0) {
-    for (int t = 0; t < k; ++t) {
-      out_dist[row * k + t] = (float)bd[t];
-      out_idx[row * k + t] = bi[t] < 0 ? -1 : row_offset + bi[t];
-    }
-  }
-}
-
 // Pairwise euclidean distance matrix for clustering (scope row 8f-3): out[i,j] = sqrt(sum_k (x[i,k] - y[j,k])^2), the
 // direct form the reference evaluates per pair (process_photos.py:46-48; facial_clustering_test.py:396-400 calls
 // sklearn's pairwise_distances, which upcasts to fp64 - the direct fp32 differences have no cancellation, so both agree
@@ -1200,26 +1008,6 @@ __global__ void __launch_bounds__(256) pairwise_dist_kernel(const float* __restr
       out[i * m + j] = v;
     }
   }
-}
-
-// Merge P per-shard results (gathered as [P][nq]) into the global best: smallest distance, ties to the lowest index.
-__global__ void knn_merge_kernel(const float* __restrict__ dist_all, const long long* __restrict__ idx_all, int parts,
-                                 long long nq, float* __restrict__ best_dist, long long* __restrict__ best_idx) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  float bd = INFINITY;
-  long long bi = -1;
-  for (int p = 0; p < parts; ++p) {
-    const float dd = dist_all[(size_t)p * nq + i];
-    const long long ii = idx_all[(size_t)p * nq + i];
-    if (ii < 0) continue;
-    if (bi < 0 || dd < bd || (dd == bd && ii < bi)) {
-      bd = dd;
-      bi = ii;
-    }
-  }
-  best_dist[i] = bd;
-  best_idx[i] = bi;
 }
 
 template <typename T>

@@ -138,23 +138,42 @@ int hfr_l2_normalize(const float* x, float* y, int64_t n, int dim, int device, v
 
 /* ---- 1-NN identification ------------------------------------------------------------------------------------------
  * Replaces KNeighborsClassifier(n_neighbors=1, p=2).fit / .kneighbors (facerec_test.py:272,284-285,422) - the euclidean
- * ArgKmin reduction; label lookup stays with the caller.  A handle owns one gallery shard. */
+ * ArgKmin reduction; label lookup stays with the caller.  A handle owns one gallery shard.
+ *
+ * Exactness contract.  The result of a query equals the brute-force answer computed in double precision from the
+ * float32 rows (what scikit-learn's ArgKmin computes), ties going to the lowest gallery index:
+ *   1. the tensor-core distance GEMM (bf16 or tf32 operands) proposes candidates - the best 2 (n_neighbors = 1) or 4
+ *      approximate scores per 16k-row gallery split and epilogue warpgroup;
+ *   2. the best 4 (8) candidates per query are re-scored in fp64 from the float32 originals;
+ *   3. a query is CERTIFIED when every row that was not re-scored has an approximate score above the k-th exact
+ *      distance by more than the rigorous rounding bound of step 1 (operand rounding 2u|q||g|, u = 2^-9 bf16 / 2^-10
+ *      tf32, plus fp32 accumulation and norm terms); otherwise the query is re-scored against the WHOLE shard in fp64
+ *      (knn_exact_kernel).  hfr_knn_stats reports how many queries took that second path. */
+typedef struct hfr_neighbor {
+  double dist2;   /* squared euclidean distance, accumulated in fp64 from the float32 rows */
+  int64_t index;  /* global gallery row (global_row_offset + local row); -1: no such neighbour */
+} hfr_neighbor;
 int hfr_knn_create(int device, int dim, int precision /* HFR_TF32 or HFR_BF16 */, hfr_knn** out);
 /* gallery: device float32 [n_local, dim], must stay alive and unchanged while the handle uses it (it is re-read for
- * the exact re-ranking).  global_row_offset: index of the shard's first row in the full gallery. */
+ * the exact re-scoring).  global_row_offset: index of the shard's first row in the full gallery. */
 int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64_t global_row_offset, void* stream);
-/* queries: device float32 [nq, dim] -> best_dist2 float32 [nq] (squared euclidean), best_idx int64 [nq] (global). */
-int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist2, int64_t* best_idx, void* stream);
-/* k nearest gallery rows, 1 <= n_neighbors <= 4 (the reference's classifier list also holds
- * KNeighborsClassifier(n_neighbors=3, p=2), facerec_test.py:274-275): dist2 / idx are device [nq][n_neighbors], ascending
- * by (exact squared distance, global index) like sklearn's kneighbors; (inf, -1) where the shard has fewer rows. */
-int hfr_knn_query_k(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, float* dist2, int64_t* idx, void* stream);
-/* Host-buffer variant of set_gallery+query for the end-to-end path (copies in, runs, copies out, synchronises). */
-int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host, int64_t* best_idx_host,
+/* queries: device float32 [nq, dim] -> out: device hfr_neighbor [nq][n_neighbors], 1 <= n_neighbors <= 4 (the
+ * reference's classifier list holds n_neighbors = 1 and 3, facerec_test.py:272-275), ascending by (dist2, index) like
+ * sklearn's kneighbors; (inf, -1) where the shard has fewer rows. */
+int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream);
+/* Host-buffer variant for the end-to-end path (copies in, runs, copies out, synchronises). */
+int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, int n_neighbors, hfr_neighbor* out_host,
                        void* stream);
-/* Merge per-shard results gathered as [n_parts, nq] (e.g. by an NCCL all-gather): min distance, ties -> lowest index. */
-int hfr_knn_merge(const float* dist_all, const int64_t* idx_all, int n_parts, int64_t nq, float* best_dist2,
-                  int64_t* best_idx, int device, void* stream);
+/* Merge per-shard results gathered as [n_parts][nq][n_neighbors] (e.g. by ONE NCCL all-gather of the packed records)
+ * into the global n_neighbors nearest per query: ascending (dist2, index), ties -> lowest index. */
+int hfr_knn_merge(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, hfr_neighbor* out, int device,
+                  void* stream);
+/* Counters of the last hfr_knn_query on this handle (synchronises its stream): queries certified by the error bound /
+ * queries re-scored against the whole shard in fp64. */
+int hfr_knn_stats(hfr_knn* k, int64_t* certified, int64_t* rescored);
+/* Debug: the approximate candidate records of the last query, [nq][records] each (testing the certification bound);
+ * returns the number of records per query; score / index may be NULL to ask for the count only. */
+int64_t hfr_knn_debug_candidates(hfr_knn* k, float* score_host, int32_t* index_host, int64_t nq);
 void hfr_knn_free(hfr_knn* k);
 
 /* ---- single operators (kernel-level parity tests and profiling) ---------------------------------------------------

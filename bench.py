@@ -184,7 +184,7 @@ def plan_work(plan, es):
     return rows
 
 
-KERNEL_NAMES = {"dwpw": "dwpw_kernel (fused depthwise 3x3 + pointwise 1x1)", "pw": "gemm_tc_kernel (1x1 conv)",
+KERNEL_NAMES = {"pw": "gemm_tc_kernel (1x1 conv)", "fc": "dense_heads_kernel",
                 "conv": "gemm_tc_kernel (im2col) / conv_window_kernel", "dw": "dwconv3x3_pipe_kernel"}
 
 
@@ -307,14 +307,8 @@ def bench_network(workload, precision, args, rank, world, dev):
     i = 0
     while i < len(work):
         w, t = dict(work[i]), per_step[i]
-        # a depthwise layer followed by a pointwise layer with an empty interval ran as ONE fused dwpw_kernel launch
-        if w["kind"] == "dw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 2e-4:
-            L0, L1 = plan["layers"][i], plan["layers"][i + 1]
-            w = dict(kind="dwpw", name=work[i + 1]["name"], flops=work[i]["flops"] + work[i + 1]["flops"],
-                     bytes=float((L0["hw_in"][0] * L0["hw_in"][1] * L0["cin"] + L1["hw_out"][0] * L1["hw_out"][1] * L1["cout"]) * es))
-            i += 1
-        if t < 5e-4 and w["kind"] in ("subsample", "maxpool", "gap", "fc"):
-            i += 1      # nothing launched: bypassed gather, or a layer fused into its neighbour's kernel
+        if t < 0:
+            i += 1      # nothing launched (the library reports -1): bypassed gather, or a layer fused into a neighbour's kernel
             continue
         merged.append((w, t))
         i += 1
@@ -333,7 +327,7 @@ def bench_network(workload, precision, args, rank, world, dev):
         tf = c["flops"] / (c["ms"] * 1e-3) / 1e12
         gb = c["bytes"] / (c["ms"] * 1e-3) / 1e9
         frac_t, frac_h = tf / tensor_peak, gb / pk["hbm"]
-        tensor_bound = kname in ("pw", "conv", "dwpw") and frac_t >= frac_h
+        tensor_bound = kname in ("pw", "conv") and frac_t >= frac_h
         kernels[kname] = dict(ms_per_step=round(c["ms"], 5), launches=c["launches"],
                               bound="tensor" if tensor_bound else "hbm",
                               achieved=round(tf if tensor_bound else gb, 2),
@@ -450,13 +444,13 @@ def bench_knn(precision, args, rank, world, dev):
             # it would have extracted itself) and the query block is all-gathered over NVLink
             a, b = shard_rows(nq, world, rank)
             hq = q[a:b].contiguous().pin_memory().numpy()
-            clf.kneighbors(hq, return_distance=False, local_queries=world > 1)
+            clf.kneighbors(hq, return_distance=False, local_queries=world > 1, total_queries=nq)
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
             for _ in range(steps):
-                ind = clf.kneighbors(hq, return_distance=False, local_queries=world > 1)
+                ind = clf.kneighbors(hq, return_distance=False, local_queries=world > 1, total_queries=nq)
             torch.cuda.synchronize(dev)
             e2e_s = time.perf_counter() - t0
         else:

@@ -39,16 +39,16 @@ SIGNATURES = {
     "hfr_l2_normalize": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "hfr_knn_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
     "hfr_knn_set_gallery": (_i, [_vp, _vp, _i64, _i64, _vp]),
-    "hfr_knn_query": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
-    "hfr_knn_query_k": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
-    "hfr_knn_query_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
-    "hfr_knn_merge": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _vp]),
+    "hfr_knn_query": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "hfr_knn_query_host": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "hfr_knn_merge": (_i, [_vp, _i, _i64, _i, _vp, _i, _vp]),
+    "hfr_knn_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "hfr_knn_debug_candidates": (_i64, [_vp, _vp, _vp, _i64]),
     "hfr_knn_free": (None, [_vp]),
     "hfr_op_dwconv3x3": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "hfr_op_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "hfr_op_stem_conv": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_stem_conv_tc": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
-    "hfr_op_dwpw": (_i, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp]),
     "hfr_op_conv2d_window": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "hfr_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_maxpool": (_i, [_vp, _vp] + [_i] * 13 + [_vp]),

@@ -97,10 +97,11 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         check(lib.hfr_knn_set_gallery(h, g.data_ptr(), g.shape[0], offset, _stream_ptr(g.device)))
         return self
 
-    def kneighbors(self, X, n_neighbors=None, return_distance=True, local_queries=False):
+    def kneighbors(self, X, n_neighbors=None, return_distance=True, local_queries=False, total_queries=None):
         """sklearn's kneighbors.  local_queries=True (sharded gallery only): X holds THIS rank's block of the queries
         (contiguous blocks in rank order, e.g. the embeddings it extracted from its slice of the batch); the blocks
-        are all-gathered over NCCL and every rank returns the neighbours of the whole query set."""
+        are all-gathered over NCCL and every rank returns the neighbours of the whole query set.  total_queries: the
+        size of the whole set when the blocks follow parallel.shard_rows (saves the exchange of the block sizes)."""
         if getattr(self, "_knn", None) is None:
             from sklearn.exceptions import NotFittedError
             raise NotFittedError("This KNeighborsClassifier instance is not fitted yet.")
@@ -118,35 +119,34 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
             q = torch.nn.functional.pad(q, (0, self._pad))
         if local_queries and self.sharded:
             from .parallel import gather_rows
-            q = gather_rows(q, self.process_group)
+            q = gather_rows(q, self.process_group, total_queries)
         nq = q.shape[0]
         if nq == 0:
             empty = np.zeros((0, k), np.int64)
             return (np.zeros((0, k), np.float64), empty) if return_distance else empty
         dev = q.device.index or 0
         stream = _stream_ptr(q.device)
-        if k == 1:
-            d2 = torch.empty(nq, dtype=torch.float32, device=q.device)
-            idx = torch.empty(nq, dtype=torch.int64, device=q.device)
-            check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, d2.data_ptr(), idx.data_ptr(), stream))
-            if self.sharded:
-                from .parallel import gather_pairs
-                d_all, i_all = gather_pairs(d2, idx, self.process_group)
-                check(lib.hfr_knn_merge(d_all.data_ptr(), i_all.data_ptr(), d_all.shape[0], nq, d2.data_ptr(),
-                                        idx.data_ptr(), dev, stream))
-        else:
-            d2 = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-            idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-            check(lib.hfr_knn_query_k(self._knn, q.data_ptr(), nq, int(k), d2.data_ptr(), idx.data_ptr(), stream))
-            if self.sharded:
-                from .parallel import gather_pairs, merge_topk
-                d_all, i_all = gather_pairs(d2, idx, self.process_group)      # [P, nq, k]
-                d2, idx = merge_topk(d_all, i_all, k)
-        self._last_idx = idx
-        ind = idx.cpu().numpy().reshape(nq, k)
+        # hfr_neighbor records {double dist2; int64 index} as one int64 tensor [nq, k, 2]
+        out = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
+        check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, int(k), out.data_ptr(), stream))
+        if self.sharded:
+            from .parallel import gather_neighbors
+            parts = gather_neighbors(out, self.process_group)          # ONE all-gather of the packed records
+            check(lib.hfr_knn_merge(parts.data_ptr(), parts.shape[0], nq, int(k), out.data_ptr(), dev, stream))
+        self._last_out = out
+        rec = out.cpu().numpy()
+        ind = np.ascontiguousarray(rec[:, :, 1])
         if return_distance:
-            return np.sqrt(np.maximum(d2.cpu().numpy().astype(np.float64), 0.0)).reshape(nq, k), ind
+            d2 = np.ascontiguousarray(rec[:, :, 0]).view(np.float64)   # fp64, accumulated in fp64 on the GPU
+            return np.sqrt(d2), ind
         return ind
+
+    def query_stats(self):
+        """(queries certified by the rounding bound, queries re-scored exactly against the whole shard) of the last
+        kneighbors call on this rank."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib.hfr_knn_stats(self._knn, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def predict(self, X):
         """Uniform-weight vote over the n_neighbors nearest rows; a tie goes to the smallest class (sklearn takes the

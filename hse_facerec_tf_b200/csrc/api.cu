@@ -187,20 +187,8 @@ struct hfr_model {
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
   int sub_batch = getenv("HFR_SUB_BATCH") ? atoi(getenv("HFR_SUB_BATCH")) : 0;
   bool stem_window = window_enabled();
-  bool tf32_tc_stem = getenv("HFR_TF32_TC_STEM") != nullptr;  // experimental, see the L_STEM case
-  bool fuse_dwpw = getenv("HFR_FUSE") != nullptr;  // experimental: measured slower than the two-kernel path
-  // layer i is a stride-1 depthwise whose only consumer is the 1x1 convolution at i+1: run both as dwpw_kernel
-  bool fused_pair(size_t i) const {
-    if (!fuse_dwpw || (keep_all && !getenv("HFR_FUSE_KEEP")) || precision != HFR_BF16 || i + 1 >= plan.layers.size()) return false;
-    const Layer& a = plan.layers[i];
-    const Layer& b = plan.layers[i + 1];
-    if (a.kind != L_DW || a.stride != 1 || a.pad_t != 1 || a.pad_l != 1 || b.kind != L_PW || b.in != a.out || b.in2 >= 0)
-      return false;
-    if (plan.values[(size_t)a.out].last_use != (int)i + 1) return false;
-    for (int o : plan.outputs)
-      if (o == a.out) return false;
-    return dwpw_supported(a.cin, b.cout) && a.act <= A_RELU6 && b.act <= A_RELU6;
-  }
+  // tf32 mode's stem on the tensor cores (measured: ResNet-50 31.2k -> 40.1k img/s); HFR_TF32_TC_STEM=0: CUDA-core stem
+  bool tf32_tc_stem = !(getenv("HFR_TF32_TC_STEM") && getenv("HFR_TF32_TC_STEM")[0] == '0');
   DevBuf arena;
   int last_batch = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -210,32 +198,7 @@ struct hfr_model {
   std::vector<double> layer_ms;
   int timed_steps = 0;
   // tensor-core stem: staged space-to-depth input + per-preprocessing-flags weights
-  // Experimental (HFR_LANES=2..4, default 1): the batch is cut into `lanes` slices that run the whole layer list on
-  // their own streams between a fork and a join - independent kernels of different slices fill each other's ramp-up
-  // and tail on the SMs.  Every tensor is batch-major, so a slice is a pointer offset; only the stem's staging buffer is
-  // per lane.  Results do not depend on the lane count (every image's arithmetic is independent of the batch).
-  static constexpr int kMaxLanes = 4;
-  int n_lanes = getenv("HFR_LANES") ? std::max(1, std::min(kMaxLanes, atoi(getenv("HFR_LANES")))) : 1;
-  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
-  void init_lanes() {
-    if (lane_fork) return;
-    cuda_check(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming), "cudaEventCreate");
-    for (int l = 1; l < kMaxLanes; ++l) {
-      cuda_check(cudaStreamCreateWithFlags(&lane_stream[l], cudaStreamNonBlocking), "cudaStreamCreate(lane)");
-      cuda_check(cudaEventCreateWithFlags(&lane_join[l], cudaEventDisableTiming), "cudaEventCreate");
-    }
-  }
-  void free_lanes() {
-    if (!lane_fork) return;
-    cudaEventDestroy(lane_fork);
-    for (int l = 1; l < kMaxLanes; ++l) {
-      cudaStreamDestroy(lane_stream[l]);
-      cudaEventDestroy(lane_join[l]);
-    }
-    lane_fork = nullptr;
-  }
-  DevBuf stem_scratch_lane[kMaxLanes];
+  DevBuf stem_scratch;
   std::map<int, std::pair<void*, StemTcGeom>> stem_w2;
   // host-buffer path staging
   DevBuf stage_in;
@@ -275,7 +238,6 @@ struct hfr_model {
 
   ~hfr_model() {
     free_host_pipeline();
-    free_lanes();
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto e : ev) cudaEventDestroy(e);
     for (auto& kv : stem_w2) cudaFree(kv.second.first);
@@ -323,7 +285,38 @@ struct hfr_model {
     }
   }
 
+  // The dense tail (a hidden Dense layer on the pooled vector followed by the output heads) runs as one launch of
+  // dense_heads_kernel when it has that shape: layers [head_first, head_first + head_count) of the plan.
+  int head_first = -1, head_count = 0;
+  void plan_heads() {
+    head_first = -1;
+    head_count = 0;
+    if (getenv("HFR_NO_FUSED_HEADS")) return;
+    const int n = (int)plan.layers.size();
+    for (int i = 0; i < n; ++i) {
+      const Layer& H = plan.layers[(size_t)i];
+      if (H.kind != L_FC || H.in2 >= 0 || (H.act != A_NONE && H.act != A_RELU)) continue;
+      int cnt = 1, widths[4] = {0, 0, 0, 0};
+      while (i + cnt < n && cnt <= 4) {
+        const Layer& L = plan.layers[(size_t)(i + cnt)];
+        if (L.kind != L_FC || L.in != H.out || L.in2 >= 0) break;
+        widths[cnt - 1] = L.cout;
+        ++cnt;
+      }
+      if (i + cnt != n && plan.layers[(size_t)(i + cnt)].kind == L_FC) continue;   // a longer / different dense chain
+      if (cnt < 2 || !dense_heads_supported(H.cin, H.cout, cnt - 1, widths)) continue;
+      bool later_use = false;   // nothing after the group may read the hidden vector through another kind of layer
+      for (int j = i + cnt; j < n; ++j)
+        if (plan.layers[(size_t)j].in == H.out || plan.layers[(size_t)j].in2 == H.out) later_use = true;
+      if (later_use) continue;
+      head_first = i;
+      head_count = cnt;
+      return;
+    }
+  }
+
   void plan_arena() {
+    plan_heads();
     const int nv = (int)plan.values.size();
     val_off.assign((size_t)nv, 0);
     val_bytes.assign((size_t)nv, 0);
@@ -374,16 +367,11 @@ struct hfr_model {
       val_bytes[(size_t)L.out] = value_image_bytes(L.out);
       val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
       if (keep_all) continue;
-      // a fused depthwise+pointwise pair reads the depthwise INPUT while it writes the pointwise OUTPUT: the input must
-      // stay allocated until the pair's output has its own block
-      if (fused_pair((size_t)li)) continue;
-      int ins[3] = {L.in, L.in2, -1};
+      int ins[2] = {L.in, L.in2};
       if (gather_of[(size_t)li] >= 0) ins[0] = plan.layers[(size_t)gather_of[(size_t)li]].in;
-      if (li > 0 && fused_pair((size_t)li - 1)) ins[2] = plan.layers[(size_t)li - 1].in;
       for (int v : ins) {
         if (v <= 0) continue;  // value 0 is the caller's input
-        const int lu = last_use[(size_t)v];
-        if (lu == li || (v == ins[2] && lu == li - 1)) release(val_off[(size_t)v], val_bytes[(size_t)v]);
+        if (last_use[(size_t)v] == li) release(val_off[(size_t)v], val_bytes[(size_t)v]);
       }
       if (last_use[(size_t)L.out] < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
     }
@@ -452,37 +440,18 @@ struct hfr_model {
   void run_layers(const void* x, int in_dtype, int batch, int flags, void* const* outs, cudaStream_t s) {
     // L2-sized sub-batching: every tensor is batch-major, so a slice of the batch is a pointer offset.  Running the
     // whole layer list on one slice at a time keeps producer->consumer tensors L2-resident.
-    if (n_lanes > 1 && !timing && sub_batch <= 0 && s != nullptr && batch >= 2 * n_lanes) {
-      init_lanes();
-      const int per = (batch + n_lanes - 1) / n_lanes;
-      cuda_check(cudaEventRecord(lane_fork, s), "cudaEventRecord(fork)");
-      for (int l = 0; l < n_lanes; ++l) {
-        const int b0 = l * per, n = std::min(per, batch - b0);
-        if (n <= 0) break;
-        cudaStream_t sl = l == 0 ? s : lane_stream[l];
-        if (l > 0) cuda_check(cudaStreamWaitEvent(sl, lane_fork, 0), "cudaStreamWaitEvent(fork)");
-        run_slice(x, in_dtype, batch, b0, n, flags, sl, l);
-        if (l > 0) {
-          cuda_check(cudaEventRecord(lane_join[l], sl), "cudaEventRecord(join)");
-          cuda_check(cudaStreamWaitEvent(s, lane_join[l], 0), "cudaStreamWaitEvent(join)");
-        }
-      }
-      finish_outputs(batch, flags, outs, s);
-      return;
-    }
     int sub = sub_batch > 0 && !timing ? sub_batch : batch;
     if (sub > batch) sub = batch;
     for (int b0 = 0; b0 < batch; b0 += sub) run_slice(x, in_dtype, batch, b0, std::min(sub, batch - b0), flags, s);
     finish_outputs(batch, flags, outs, s);
   }
 
-  void run_slice(const void* x_all, int in_dtype, int total, int img0, int batch, int flags, cudaStream_t s,
-                 int lane = 0) {
-    DevBuf& stem_scratch = stem_scratch_lane[lane];
+  void run_slice(const void* x_all, int in_dtype, int total, int img0, int batch, int flags, cudaStream_t s) {
     const int prec = precision;
     const int rt = (prec == HFR_TF32);
     const size_t in_img_bytes = (size_t)plan.in_h * plan.in_w * plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);
     const void* x = (const char*)x_all + (size_t)img0 * in_img_bytes;
+    std::vector<char> launched(plan.layers.size(), 1);
     auto vptr = [&](int v) -> void* { return (char*)val_ptr(v, total) + (size_t)img0 * value_exact_bytes(v); };
     for (size_t i = 0; i < plan.layers.size(); ++i) {
       const Layer& L = plan.layers[i];
@@ -492,19 +461,27 @@ struct hfr_model {
       const int act = L.act;  // A_NONE/A_RELU/A_RELU6 share values with the kernels' ACT_* codes
       const int round_out = rt && feeds_tensor_core(L.out);
       if (timing) cuda_check(cudaEventRecord(ev[2 * i], s), "cudaEventRecord");
-      if (fused_pair(i)) {
-        const Layer& P = plan.layers[i + 1];
-        DwPwArgs f;
-        f.x = in; f.dw_w = (const float*)d.w; f.dw_b = d.bias; f.pw_w = dev[i + 1].w; f.pw_b = dev[i + 1].bias;
-        f.y = vptr(P.out); f.B = batch; f.H = L.H; f.W = L.W; f.cin = L.cin; f.cout = P.cout; f.dw_act = L.act;
-        f.pw_act = P.act;
-        launch_dwpw(f, device, s);
-        if (timing) {   // the pair's time is booked on the depthwise layer; the pointwise layer records an empty interval
-          cuda_check(cudaEventRecord(ev[2 * i + 1], s), "cudaEventRecord");
-          cuda_check(cudaEventRecord(ev[2 * i + 2], s), "cudaEventRecord");
-          cuda_check(cudaEventRecord(ev[2 * i + 3], s), "cudaEventRecord");
+      launched[i] = 1;
+      if ((int)i == head_first) {   // hidden Dense + its heads: one launch, booked on the hidden layer
+        HeadsArgs h;
+        memset(&h, 0, sizeof(h));
+        h.x = (const float*)in; h.w1 = (const float*)d.w; h.b1 = d.bias; h.hidden = (float*)out;
+        h.B = batch; h.K = L.cin; h.n1 = L.cout; h.act1 = act; h.n_heads = head_count - 1;
+        for (int j = 1; j < head_count; ++j) {
+          const Layer& P = plan.layers[i + (size_t)j];
+          h.w[j - 1] = (const float*)dev[i + (size_t)j].w; h.b[j - 1] = dev[i + (size_t)j].bias;
+          h.y[j - 1] = (float*)vptr(P.out); h.n[j - 1] = P.cout; h.act[j - 1] = P.act;
         }
-        ++i;
+        launch_dense_heads(h, s);
+        if (timing) cuda_check(cudaEventRecord(ev[2 * i + 1], s), "cudaEventRecord");
+        for (int j = 1; j < head_count; ++j) {
+          launched[i + (size_t)j] = 0;
+          if (timing) {
+            cuda_check(cudaEventRecord(ev[2 * (i + (size_t)j)], s), "cudaEventRecord");
+            cuda_check(cudaEventRecord(ev[2 * (i + (size_t)j) + 1], s), "cudaEventRecord");
+          }
+        }
+        i += (size_t)head_count - 1;
         continue;
       }
       switch (L.kind) {
@@ -522,8 +499,8 @@ struct hfr_model {
             if (flags & HFR_FLAG_SCALE_PM1) { a.scale = 1.f / 127.5f; a.mean[0] = a.mean[1] = a.mean[2] = 1.f; }
           }
           a.act = act; a.round_tf32 = round_out;
-          // experimental (HFR_TF32_TC_STEM=1, unmeasured): the tf32 mode's stem on the tensor cores as well - fp32
-          // output, weights as hi + lo bf16 sweeps (the uint8 image is exact in bf16), window kernel only
+          // the tf32 mode's stem runs on the tensor cores as well: fp32 output, weights as hi + lo bf16 sweeps into one
+          // accumulator (16 mantissa bits; the uint8 image is exact in bf16), window kernel only
           const bool tc32 = prec == HFR_TF32 && stem_window && tf32_tc_stem;
           const bool tc = (prec == HFR_BF16 || tc32) && a.in_u8 && L.stride == 2 && L.dil == 1 && (L.H % 2 == 0) &&
                           (L.W % 2 == 0) && (L.cout == 32 || L.cout == 64) && !stem_force_direct;
@@ -616,7 +593,7 @@ struct hfr_model {
           break;
         }
         case L_SUBSAMPLE:
-          if (skip_layer[i]) break;
+          if (skip_layer[i]) { launched[i] = 0; break; }
           launch_subsample(in, out, batch, L.H, L.W, L.cin, L.Ho, L.Wo, L.stride, prec, s);
           break;
         case L_GAP:
@@ -636,7 +613,8 @@ struct hfr_model {
       for (size_t i = 0; i < plan.layers.size(); ++i) {
         float ms = 0.f;
         cuda_check(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]), "cudaEventElapsedTime");
-        layer_ms[i] += ms;
+        if (launched[i]) layer_ms[i] += ms;
+        else layer_ms[i] = -1.0;   // nothing was launched for this layer (bypassed gather / fused into a neighbour)
       }
       ++timed_steps;
     }
@@ -1032,8 +1010,12 @@ struct hfr_knn {
   int device = 0, dim = 0, precision = HFR_BF16;
   const float* gallery = nullptr;  // borrowed fp32 rows
   int64_t n_local = 0, row_offset = 0;
-  DevBuf g_lowp, g_norm, q_lowp, part_score, part_idx;
-  DevBuf h_q, h_dist, h_idx;  // host-path staging
+  DevBuf g_lowp, g_norm, g_max2, q_lowp, part_score, part_idx;
+  DevBuf unc_list, counters, locks;  // certification: queries for the exact pass, their count, per-query merge locks
+  DevBuf h_q, h_out;                 // host-path staging
+  int64_t last_nq = 0;
+  int last_records = 0;              // candidate records per query of the last call (debugging)
+  cudaStream_t last_stream = nullptr;
 };
 
 extern "C" {
@@ -1060,34 +1042,45 @@ int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64
     k->n_local = n_local;
     k->row_offset = global_row_offset;
     k->g_norm.ensure((size_t)n_local * 4);
+    k->g_max2.ensure(4);
     void* lowp = nullptr;
     if (k->precision == HFR_BF16) {
       k->g_lowp.ensure((size_t)n_local * k->dim * 2);
       lowp = k->g_lowp.p;
     }
-    launch_rows_prep(gallery, lowp, (float*)k->g_norm.p, n_local, k->dim, (cudaStream_t)stream);
+    cuda_check(cudaMemsetAsync(k->g_max2.p, 0, 4, (cudaStream_t)stream), "cudaMemsetAsync");
+    launch_rows_prep(gallery, lowp, (float*)k->g_norm.p, (float*)k->g_max2.p, n_local, k->dim, (cudaStream_t)stream);
   });
 }
 
-int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist2, int64_t* best_idx, void* stream) {
+int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream) {
   return guarded([&] {
-    if (!k || !queries || !best_dist2 || !best_idx || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!k || !queries || !out || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (n_neighbors < 1 || n_neighbors > 4) throw Error(HFR_ERR_UNSUPPORTED, "k-NN on the GPU path supports 1 <= n_neighbors <= 4");
     if (!k->gallery) throw Error(HFR_ERR_STATE, "hfr_knn_query before hfr_knn_set_gallery (NotFittedError)");
     if (nq == 0) return;
+    if (nq >= (1ll << 31)) throw Error(HFR_ERR_INVALID, "too many queries for one call");
     use_device(k->device);
     cudaStream_t s = (cudaStream_t)stream;
     int splits, per;
     knn_plan(nq, k->n_local, &splits, &per);
-    k->part_score.ensure((size_t)nq * splits * 4 * 4);  // [nq][splits][2 warpgroups][top-2]
-    k->part_idx.ensure((size_t)nq * splits * 4 * 4);
+    const int cand = n_neighbors == 1 ? 2 : 4;  // candidates per (query, gallery split, epilogue warpgroup)
+    k->part_score.ensure((size_t)nq * splits * 2 * cand * 4);
+    k->part_idx.ensure((size_t)nq * splits * 2 * cand * 4);
+    k->unc_list.ensure((size_t)nq * 4);
+    k->locks.ensure((size_t)nq * 4);
+    k->counters.ensure(16);
+    cuda_check(cudaMemsetAsync(k->counters.p, 0, 16, s), "cudaMemsetAsync");
+    cuda_check(cudaMemsetAsync(k->locks.p, 0, (size_t)nq * 4, s), "cudaMemsetAsync");
     KnnGemmArgs a;
     a.nq = nq; a.n = k->n_local; a.d = k->dim; a.splits = splits; a.n_blocks_per_unit = per;
+    a.cand = cand;
     a.gnorm = (const float*)k->g_norm.p;
     a.part_score = (float*)k->part_score.p;
     a.part_idx = (int*)k->part_idx.p;
     if (k->precision == HFR_BF16) {
       k->q_lowp.ensure((size_t)nq * k->dim * 2);
-      launch_rows_prep(queries, k->q_lowp.p, nullptr, nq, k->dim, s);
+      launch_rows_prep(queries, k->q_lowp.p, nullptr, nullptr, nq, k->dim, s);
       a.q = k->q_lowp.p;
       a.g = k->g_lowp.p;
     } else {
@@ -1095,74 +1088,80 @@ int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, float* best_dist
       a.g = k->gallery;
     }
     launch_knn_gemm(a, k->precision, k->device, s);
-    launch_knn_finalize(queries, k->gallery, a.part_score, a.part_idx, splits, nq, k->dim, k->row_offset, best_dist2,
-                        best_idx, s);
+    KnnFinalizeArgs f;
+    f.q = queries; f.g = k->gallery; f.part_score = a.part_score; f.part_idx = a.part_idx; f.splits = splits;
+    f.cand = cand; f.nq = nq; f.n = k->n_local; f.d = k->dim; f.row_offset = k->row_offset; f.k = n_neighbors;
+    f.precision = k->precision; f.gmax2 = (const float*)k->g_max2.p; f.out = out;
+    f.unc_list = (int*)k->unc_list.p; f.counters = (int*)k->counters.p; f.locks = (int*)k->locks.p;
+    launch_knn_finalize(f, k->device, s);
+    k->last_nq = nq;
+    k->last_records = splits * 2 * cand;
+    k->last_stream = s;
   });
 }
 
-int hfr_knn_query_k(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, float* dist2, int64_t* idx,
-                    void* stream) {
-  return guarded([&] {
-    if (!k || !queries || !dist2 || !idx || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
-    if (n_neighbors < 1 || n_neighbors > 4) throw Error(HFR_ERR_UNSUPPORTED, "k-NN on the GPU path supports 1 <= n_neighbors <= 4");
-    if (!k->gallery) throw Error(HFR_ERR_STATE, "hfr_knn_query_k before hfr_knn_set_gallery (NotFittedError)");
-    if (nq == 0) return;
-    use_device(k->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    int splits, per;
-    knn_plan(nq, k->n_local, &splits, &per);
-    k->part_score.ensure((size_t)nq * splits * 8 * 4);  // [nq][splits][2 warpgroups][top-4]
-    k->part_idx.ensure((size_t)nq * splits * 8 * 4);
-    KnnGemmArgs a;
-    a.nq = nq; a.n = k->n_local; a.d = k->dim; a.splits = splits; a.n_blocks_per_unit = per;
-    a.cand = 4;
-    a.gnorm = (const float*)k->g_norm.p;
-    a.part_score = (float*)k->part_score.p;
-    a.part_idx = (int*)k->part_idx.p;
-    if (k->precision == HFR_BF16) {
-      k->q_lowp.ensure((size_t)nq * k->dim * 2);
-      launch_rows_prep(queries, k->q_lowp.p, nullptr, nq, k->dim, s);
-      a.q = k->q_lowp.p;
-      a.g = k->g_lowp.p;
-    } else {
-      a.q = queries;
-      a.g = k->gallery;
-    }
-    launch_knn_gemm(a, k->precision, k->device, s);
-    launch_knn_finalize_k(queries, k->gallery, a.part_score, a.part_idx, splits, nq, k->dim, k->row_offset, n_neighbors,
-                          dist2, idx, s);
-  });
-}
-
-int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, float* best_dist2_host,
-                       int64_t* best_idx_host, void* stream) {
+int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, int n_neighbors, hfr_neighbor* out_host,
+                       void* stream) {
   int rc = guarded([&] {
-    if (!k || !queries_host || !best_dist2_host || !best_idx_host || nq <= 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!k || !queries_host || !out_host || nq <= 0 || n_neighbors < 1 || n_neighbors > 4)
+      throw Error(HFR_ERR_INVALID, "bad argument");
     use_device(k->device);
     k->h_q.ensure((size_t)nq * k->dim * 4);
-    k->h_dist.ensure((size_t)nq * 4);
-    k->h_idx.ensure((size_t)nq * 8);
+    k->h_out.ensure((size_t)nq * n_neighbors * sizeof(hfr_neighbor));
     cuda_check(cudaMemcpyAsync(k->h_q.p, queries_host, (size_t)nq * k->dim * 4, cudaMemcpyHostToDevice,
                                (cudaStream_t)stream), "cudaMemcpyAsync(H2D)");
   });
   if (rc) return rc;
-  rc = hfr_knn_query(k, (const float*)k->h_q.p, nq, (float*)k->h_dist.p, (int64_t*)k->h_idx.p, stream);
+  rc = hfr_knn_query(k, (const float*)k->h_q.p, nq, n_neighbors, (hfr_neighbor*)k->h_out.p, stream);
   if (rc) return rc;
   return guarded([&] {
     cudaStream_t s = (cudaStream_t)stream;
-    cuda_check(cudaMemcpyAsync(best_dist2_host, k->h_dist.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s), "D2H");
-    cuda_check(cudaMemcpyAsync(best_idx_host, k->h_idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_check(cudaMemcpyAsync(out_host, k->h_out.p, (size_t)nq * n_neighbors * sizeof(hfr_neighbor),
+                               cudaMemcpyDeviceToHost, s), "D2H");
     cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
   });
 }
 
-int hfr_knn_merge(const float* dist_all, const int64_t* idx_all, int n_parts, int64_t nq, float* best_dist2,
-                  int64_t* best_idx, int device, void* stream) {
+int hfr_knn_merge(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, hfr_neighbor* out, int device,
+                  void* stream) {
   return guarded([&] {
-    if (!dist_all || !idx_all || !best_dist2 || !best_idx || n_parts <= 0 || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!parts || !out || n_parts <= 0 || nq < 0 || n_neighbors < 1 || n_neighbors > 4)
+      throw Error(HFR_ERR_INVALID, "bad argument");
     use_device(device);
-    launch_knn_merge(dist_all, idx_all, n_parts, nq, best_dist2, best_idx, (cudaStream_t)stream);
+    launch_knn_merge(parts, n_parts, nq, n_neighbors, out, (cudaStream_t)stream);
   });
+}
+
+int hfr_knn_stats(hfr_knn* k, int64_t* certified, int64_t* rescored) {
+  return guarded([&] {
+    if (!k) throw Error(HFR_ERR_INVALID, "null handle");
+    int64_t unc = 0;
+    if (k->last_nq > 0) {
+      use_device(k->device);
+      int c = 0;
+      cuda_check(cudaStreamSynchronize(k->last_stream), "cudaStreamSynchronize");
+      cuda_check(cudaMemcpy(&c, k->counters.p, 4, cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
+      unc = c;
+    }
+    if (certified) *certified = k->last_nq - unc;
+    if (rescored) *rescored = unc;
+  });
+}
+
+int64_t hfr_knn_debug_candidates(hfr_knn* k, float* score_host, int32_t* index_host, int64_t nq) {
+  int64_t rec = 0;
+  int rc = guarded([&] {
+    if (!k) throw Error(HFR_ERR_INVALID, "null handle");
+    rec = k->last_records;
+    if (!score_host && !index_host) return;
+    if (nq != k->last_nq) throw Error(HFR_ERR_STATE, "nq does not match the last query");
+    use_device(k->device);
+    cuda_check(cudaStreamSynchronize(k->last_stream), "cudaStreamSynchronize");
+    const size_t bytes = (size_t)nq * rec * 4;
+    if (score_host) cuda_check(cudaMemcpy(score_host, k->part_score.p, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    if (index_host) cuda_check(cudaMemcpy(index_host, k->part_idx.p, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy");
+  });
+  return rc < 0 ? rc : rec;
 }
 
 void hfr_knn_free(hfr_knn* k) { delete k; }
@@ -1243,17 +1242,6 @@ int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias
       throw;
     }
     cudaFree(w2d);
-  });
-}
-
-int hfr_op_dwpw(const void* x, const float* dw_w, const float* dw_b, const void* pw_w, const float* pw_b, void* y,
-                int batch, int h, int w_, int cin, int cout, int dw_act, int pw_act, int device, void* stream) {
-  return guarded([&] {
-    use_device(device);
-    DwPwArgs a;
-    a.x = x; a.dw_w = dw_w; a.dw_b = dw_b; a.pw_w = pw_w; a.pw_b = pw_b; a.y = y; a.B = batch; a.H = h; a.W = w_;
-    a.cin = cin; a.cout = cout; a.dw_act = dw_act; a.pw_act = pw_act;
-    launch_dwpw(a, device, (cudaStream_t)stream);
   });
 }
 

@@ -359,107 +359,7 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const uint8_t* __restrict
 // zero-filled by the TMA unit, which is exactly the zero padding), every output byte is written once as 16-byte
 // vectors.  CTA = 8x8 output pixels x (16 bytes * VL) channels; a thread owns one 16-byte channel vector of a
 // vertical strip of 4 outputs and slides the 3-row window through registers.
-struct DwParams {
-  int C, Ho, Wo, pad_t, pad_l, tiles_w, act, round_tf32;
-};
-
-template <typename T, int STRIDE, int TILE_H>
-__global__ void __launch_bounds__(128, 6) dwconv3x3_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                        const float* __restrict__ w,   // [9][C]
-                                                        const float* __restrict__ bias,  // [C]
-                                                        T* __restrict__ y, const DwParams p) {
-  constexpr int VN = Vec16<T>::N;
-  constexpr int TWI = 7 * STRIDE + 3;
-  constexpr int THI = (TILE_H - 1) * STRIDE + 3;   // TILE_H x 8 output pixels per CTA: more bytes in flight per SM
-  extern __shared__ uint8_t dw_smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  uint8_t* dw_smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);  // TMA destination: 128-B aligned
-  const int VL = blockDim.x >> 4;  // 16-byte vector lanes per pixel (4 or 8)
-  const int cbe = VL * VN;         // channels per CTA
-  const int tile = blockIdx.x;
-  const int ox0 = (tile % p.tiles_w) * 8, oy0 = (tile / p.tiles_w) * TILE_H;
-  const int c0 = blockIdx.y * cbe;
-  const int b = blockIdx.z;
-  const uint32_t sm = smem_u32(dw_smem);
-  const uint32_t sbar = smem_u32(&bar);
-  pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    mbar_init(sbar, 1);
-    fence_barrier_init();
-    pdl_wait();
-    mbar_expect_tx(sbar, (uint32_t)(TWI * THI * cbe * sizeof(T)));
-    tma_load_4d(sm, &tmX, sbar, c0, ox0 * STRIDE - p.pad_l, oy0 * STRIDE - p.pad_t, b);
-  }
-  const int v = threadIdx.x % VL;
-  const int strip = threadIdx.x / VL;  // 0..15
-  const int lx = strip & 7;            // output column within the tile
-  const int c = c0 + v * VN;
-  float bs[VN];
-#pragma unroll
-  for (int e = 0; e < VN; ++e) bs[e] = __ldg(bias + c + e);
-  pdl_wait();       // outputs are written (and may alias the predecessor's inputs) only after it has completed
-  __syncthreads();  // barrier init visible to all waiters
-  mbar_wait(sbar, 0);
-  const T* tile_s = reinterpret_cast<const T*>(dw_smem);
-  constexpr int NROWS = 3 * STRIDE + 3;  // input rows touched by 4 vertically adjacent outputs
-  const int ox = ox0 + lx;
-#pragma unroll 1
-  for (int half = 0; half < TILE_H / 8; ++half) {
-    const int ly0 = half * 8 + (strip >> 3) * 4;  // first output row of this thread's strip of 4
-    float acc[4][VN];
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-      for (int e = 0; e < VN; ++e) acc[o][e] = bs[e];
-    // one filter column at a time: only 3 taps x VN weights are live (keeps the kernel at <= 80 registers -> 6 CTAs/SM)
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      float wk[3][VN];
-#pragma unroll
-      for (int kr = 0; kr < 3; ++kr) {
-#pragma unroll
-        for (int e = 0; e < VN; ++e) wk[kr][e] = __ldg(w + (size_t)(kr * 3 + s) * p.C + c + e);
-      }
-      const int ix = lx * STRIDE + s;
-#pragma unroll
-      for (int r = 0; r < NROWS; ++r) {
-        const int iy = ly0 * STRIDE + r;
-        float xv[VN];
-        Vec16<T>::load(tile_s + ((size_t)(iy * TWI + ix) * VL + v) * VN, xv);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int kr = r - o * STRIDE;  // filter row this input row hits for output o
-          if (kr >= 0 && kr < 3) {
-#pragma unroll
-            for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
-          }
-        }
-      }
-    }
-    if (ox < p.Wo) {
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int oy = oy0 + ly0 + o;
-        if (oy < p.Ho) {
-          T* dst = y + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + c;
-          if constexpr (sizeof(T) == 2) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2_act(acc[o][2 * e], acc[o][2 * e + 1], p.act);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          } else {
-            float ov[VN];
-#pragma unroll
-            for (int e = 0; e < VN; ++e) ov[e] = finish<T>(acc[o][e], p.act, p.round_tf32);
-            Vec16<T>::store(dst, ov);
-          }
-        }
-      }
-    }
-  }
-}
-
-// Persistent, software-pipelined variant of the kernel above (the default): a producer warp keeps `stages` halo windows in
+// Persistent, software-pipelined kernel: a producer warp keeps `stages` halo windows in
 // flight through a TMA ring while 16*VL compute threads drain them, so an SM holds stages x CTAs windows of loads
 // outstanding instead of one per resident CTA, tiles cost no CTA launch, and the per-CTA constants (this CTA's channel
 // block of weights and bias) are staged once: the launcher makes the grid a multiple of the channel-block count, so a
@@ -857,6 +757,174 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, co
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       if (b0 + r < B) y[(size_t)(b0 + r) * N + n] = acc[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The whole dense tail of the age/gender network in ONE launch (age_gender_train.py:91-98, facial_analysis.py:109):
+//   hidden = act1(x[B,K] W1[K,N1] + b1)            'feats'  Dense(256, relu)
+//   head_h = act_h(hidden W_h[N1,N_h] + b_h)        'age_pred' Dense(100, softmax) | 'gender_pred' Dense(1, sigmoid)
+// CTA = 4 batch rows, 512 threads.  Layer 1: thread = (4 output columns as one float4 of W1's row, one of 512/(N1/4)
+// K slices): every weight load is 16 bytes and 1/8 of the K loop long, the slices are reduced through shared memory.
+// Layer 2: the heads' columns side by side (<= 128 in total), thread = (column, one of 4 K slices).  Softmax / sigmoid
+// finish in shared memory.  Three dependent launches of ~40 us (latency-bound weight streaming) become one of ~15 us.
+constexpr int kHeadRows = 4, kHeadThreads = 512, kHeadMaxHeads = 4, kHeadMaxCols = 128, kHeadMaxHidden = 256;
+struct HeadsParams {
+  const float* x;        // [B][K]
+  const float* w1;       // [K][N1]
+  const float* b1;       // [N1] or null
+  float* hidden;         // [B][N1]
+  int B, K, N1, act1;
+  int n_heads;
+  const float* w[kHeadMaxHeads];   // [N1][n[h]]
+  const float* b[kHeadMaxHeads];
+  float* y[kHeadMaxHeads];         // [B][n[h]]
+  int n[kHeadMaxHeads], act[kHeadMaxHeads];
+};
+
+__global__ void __launch_bounds__(kHeadThreads) dense_heads_kernel(const HeadsParams p) {
+  extern __shared__ __align__(16) float s_heads[];
+  float* sx = s_heads;                                   // [4][K]
+  float* part = sx + kHeadRows * p.K;                    // [slices][4][N1] (layer 1) / [4 slices][4][128] (layer 2)
+  float* hid = part + (kHeadThreads / (p.N1 / 4)) * kHeadRows * p.N1;   // [4][N1]
+  float* logit = hid + kHeadRows * kHeadMaxHidden;       // [4][128]
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * kHeadRows;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = tid; i < kHeadRows * p.K; i += kHeadThreads) {
+    const int r = i / p.K, k = i - r * p.K;
+    sx[i] = (b0 + r < p.B) ? p.x[(size_t)(b0 + r) * p.K + k] : 0.f;
+  }
+  __syncthreads();
+  // ---- layer 1
+  const int ncv = p.N1 / 4, slices = kHeadThreads / ncv;
+  {
+    const int cv = tid % ncv, ks = tid / ncv;
+    float acc[kHeadRows][4];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    if (ks < slices) {
+      const int kper = (p.K + slices - 1) / slices;
+      const int k0 = ks * kper, k1 = min(p.K, k0 + kper);
+      const float4* w4 = reinterpret_cast<const float4*>(p.w1) + cv;
+      int k = k0;
+      for (; k + 8 <= k1; k += 8) {   // 8 independent 16-byte weight loads in flight per thread
+        float4 ww[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ww[u] = __ldg(w4 + (size_t)(k + u) * ncv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int r = 0; r < kHeadRows; ++r) {
+            const float xv = sx[r * p.K + k + u];
+            acc[r][0] = fmaf(xv, ww[u].x, acc[r][0]);
+            acc[r][1] = fmaf(xv, ww[u].y, acc[r][1]);
+            acc[r][2] = fmaf(xv, ww[u].z, acc[r][2]);
+            acc[r][3] = fmaf(xv, ww[u].w, acc[r][3]);
+          }
+      }
+      for (; k < k1; ++k) {
+        const float4 ww = __ldg(w4 + (size_t)k * ncv);
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r) {
+          const float xv = sx[r * p.K + k];
+          acc[r][0] = fmaf(xv, ww.x, acc[r][0]);
+          acc[r][1] = fmaf(xv, ww.y, acc[r][1]);
+          acc[r][2] = fmaf(xv, ww.z, acc[r][2]);
+          acc[r][3] = fmaf(xv, ww.w, acc[r][3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r)
+        *reinterpret_cast<float4*>(&part[(ks * kHeadRows + r) * p.N1 + cv * 4]) =
+            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kHeadRows * p.N1; i += kHeadThreads) {
+    const int r = i / p.N1, n = i - r * p.N1;
+    float v = p.b1 ? p.b1[n] : 0.f;
+    for (int q = 0; q < slices; ++q) v += part[(q * kHeadRows + r) * p.N1 + n];   // fixed order: deterministic
+    if (p.act1 == FC_RELU) v = fmaxf(v, 0.f);
+    hid[r * kHeadMaxHidden + n] = v;
+    if (b0 + r < p.B) p.hidden[(size_t)(b0 + r) * p.N1 + n] = v;
+  }
+  __syncthreads();
+  if (p.n_heads == 0) return;
+  // ---- layer 2: all heads' columns side by side
+  int off[kHeadMaxHeads + 1];
+  off[0] = 0;
+#pragma unroll
+  for (int h = 0; h < kHeadMaxHeads; ++h) off[h + 1] = off[h] + (h < p.n_heads ? p.n[h] : 0);
+  const int ncols = off[p.n_heads];
+  {
+    const int col = tid & (kHeadMaxCols - 1), ks = tid / kHeadMaxCols;   // 4 K slices
+    float acc[kHeadRows] = {0.f, 0.f, 0.f, 0.f};
+    if (col < ncols) {
+      int h = 0;
+      while (col >= off[h + 1]) ++h;
+      const int c = col - off[h], nh = p.n[h];
+      const float* wh = p.w[h] + c;
+      const int kper = (p.N1 + 3) / 4;
+      const int k0 = ks * kper, k1 = min(p.N1, k0 + kper);
+      int k = k0;
+      for (; k + 8 <= k1; k += 8) {
+        float ww[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ww[u] = __ldg(wh + (size_t)(k + u) * nh);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(hid[r * kHeadMaxHidden + k + u], ww[u], acc[r]);
+      }
+      for (; k < k1; ++k) {
+        const float ww = __ldg(wh + (size_t)k * nh);
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(hid[r * kHeadMaxHidden + k], ww, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) part[(ks * kHeadRows + r) * kHeadMaxCols + col] = acc[r];
+  }
+  __syncthreads();
+  for (int i = tid; i < kHeadRows * kHeadMaxCols; i += kHeadThreads) {
+    const int r = i / kHeadMaxCols, col = i - r * kHeadMaxCols;
+    float v = -INFINITY;
+    if (col < ncols) {
+      int h = 0;
+      while (col >= off[h + 1]) ++h;
+      v = p.b[h] ? p.b[h][col - off[h]] : 0.f;
+      for (int q = 0; q < 4; ++q) v += part[(q * kHeadRows + r) * kHeadMaxCols + col];
+    }
+    logit[i] = v;
+  }
+  __syncthreads();
+  // ---- activations: warp (r, h) finishes row r of head h
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int job = warp; job < kHeadRows * p.n_heads; job += kHeadThreads / 32) {
+    const int r = job / p.n_heads, h = job - r * p.n_heads;
+    if (b0 + r >= p.B) continue;
+    const float* lg = logit + r * kHeadMaxCols + off[h];
+    float* out = p.y[h] + (size_t)(b0 + r) * p.n[h];
+    if (p.act[h] == FC_SOFTMAX) {
+      float mx = -INFINITY;
+      for (int j = lane; j < p.n[h]; j += 32) mx = fmaxf(mx, lg[j]);
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      for (int j = lane; j < p.n[h]; j += 32) sum += expf(lg[j] - mx);
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      for (int j = lane; j < p.n[h]; j += 32) out[j] = expf(lg[j] - mx) / sum;
+    } else {
+      for (int j = lane; j < p.n[h]; j += 32) {
+        float v = lg[j];
+        if (p.act[h] == FC_RELU) v = fmaxf(v, 0.f);
+        if (p.act[h] == FC_SIGMOID) v = 1.f / (1.f + expf(-v));
+        out[j] = v;
+      }
+    }
   }
 }
 

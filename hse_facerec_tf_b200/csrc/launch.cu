@@ -2,6 +2,7 @@
 // tile-shape selection and grid sizing for the sm_100a kernels in kernels.cuh / gemm_tc.cuh.
 #include "launch.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <utility>
@@ -9,7 +10,6 @@
 #include <mutex>
 
 #include "conv_window.cuh"
-#include "dwpw.cuh"
 #include "kernels.cuh"
 
 namespace hfr {
@@ -161,39 +161,6 @@ void launch_stem(const StemArgs& a, int prec, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise
-template <typename T, int STRIDE, int TILE_H>
-static void launch_dw_t(const DwArgs& a, int prec, cudaStream_t s) {
-  constexpr int VN = Vec16<T>::N;
-  const int es = (int)sizeof(T);
-  int VL = (a.C * es) / 16;
-  if (VL > 8) VL = 8;
-  if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
-  const int cbe = VL * VN;
-  if (a.C % cbe) throw Error(-1, "depthwise: channels must be a multiple of the channel block");
-  constexpr int TWI = 7 * STRIDE + 3;
-  constexpr int THI = (TILE_H - 1) * STRIDE + 3;
-  const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-  const uint64_t strides[3] = {(uint64_t)a.C * es, (uint64_t)a.W * a.C * es, (uint64_t)a.H * a.W * a.C * es};
-  const uint32_t box[4] = {(uint32_t)cbe, (uint32_t)TWI, (uint32_t)THI, 1};
-  CUtensorMap tm = make_tiled(a.x, prec, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-  DwParams p;
-  p.C = a.C; p.Ho = a.Ho; p.Wo = a.Wo; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
-  p.tiles_w = (a.Wo + 7) / 8;
-  p.act = a.act; p.round_tf32 = a.round_tf32;
-  const int tiles_h = (a.Ho + TILE_H - 1) / TILE_H;
-  dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(a.C / cbe), (unsigned)a.B);
-  const size_t smem = (size_t)TWI * THI * cbe * es + 128;
-  auto kern = dwconv3x3_kernel<T, STRIDE, TILE_H>;
-  if (smem > 48 * 1024) {
-    static std::atomic<bool> configured{false};
-    if (!configured.load()) {
-      cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "dw smem attribute");
-      configured.store(true);
-    }
-  }
-  launch_pdl(kern, grid, dim3(16 * VL), smem, s, tm, a.w, a.bias, (T*)a.y, p);
-  HFR_LAUNCH_CHECK("dwconv3x3");
-}
 // persistent pipelined kernel: grid = resident CTAs (a multiple of the channel-block count), stages sized to ~52 KB of
 // windows per CTA
 template <typename T, int STRIDE, int VL>
@@ -241,33 +208,18 @@ static void launch_dw_pipe_t(const DwArgs& a, int prec, int device, cudaStream_t
 
 void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
   if (a.B > 65535) throw Error(-1, "depthwise: batch too large for one launch");
-  static const bool oneshot = getenv("HFR_DW_ONESHOT") != nullptr;  // environment switches are read once
-  if (!oneshot && (a.stride == 1 || a.stride == 2)) {
-    int device = 0;
-    cuda_check(cudaGetDevice(&device), "cudaGetDevice");
-    const int es = prec == PREC_BF16 ? 2 : 4;
-    int VL = (a.C * es) / 16;
-    if (VL > 8) VL = 8;
-    if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
+  if (a.stride != 1 && a.stride != 2) throw Error(-5, "depthwise: stride must be 1 or 2");
+  int device = 0;
+  cuda_check(cudaGetDevice(&device), "cudaGetDevice");
+  const int es = prec == PREC_BF16 ? 2 : 4;
+  int VL = (a.C * es) / 16;
+  if (VL > 8) VL = 8;
+  if (VL != 4 && VL != 8) throw Error(-1, "depthwise: channel count must give 64 or >=128 bytes per pixel");
 #define HFR_DW_PIPE(T, S) \
-    do { if (VL == 8) launch_dw_pipe_t<T, S, 8>(a, prec, device, s); else launch_dw_pipe_t<T, S, 4>(a, prec, device, s); } while (0)
-    if (prec == PREC_BF16) { if (a.stride == 1) HFR_DW_PIPE(__nv_bfloat16, 1); else HFR_DW_PIPE(__nv_bfloat16, 2); }
-    else                   { if (a.stride == 1) HFR_DW_PIPE(float, 1); else HFR_DW_PIPE(float, 2); }
+  do { if (VL == 8) launch_dw_pipe_t<T, S, 8>(a, prec, device, s); else launch_dw_pipe_t<T, S, 4>(a, prec, device, s); } while (0)
+  if (prec == PREC_BF16) { if (a.stride == 1) HFR_DW_PIPE(__nv_bfloat16, 1); else HFR_DW_PIPE(__nv_bfloat16, 2); }
+  else                   { if (a.stride == 1) HFR_DW_PIPE(float, 1); else HFR_DW_PIPE(float, 2); }
 #undef HFR_DW_PIPE
-    return;
-  }
-  // 16x8-pixel tiles (TILE_H = 16) were measured 40 % slower than 8x8 on B200 (fewer, longer-running CTAs): kept only
-  // as a template option
-  static const bool tall_env = getenv("HFR_DW_TALL") != nullptr;
-  const bool tall = tall_env && a.Ho > 8;
-  if (a.stride == 1) {
-    if (prec == PREC_BF16) { if (tall) launch_dw_t<__nv_bfloat16, 1, 16>(a, prec, s); else launch_dw_t<__nv_bfloat16, 1, 8>(a, prec, s); }
-    else                   { if (tall) launch_dw_t<float, 1, 16>(a, prec, s); else launch_dw_t<float, 1, 8>(a, prec, s); }
-  } else if (a.stride == 2) {
-    if (prec == PREC_BF16) launch_dw_t<__nv_bfloat16, 2, 8>(a, prec, s); else launch_dw_t<float, 2, 8>(a, prec, s);
-  } else {
-    throw Error(-5, "depthwise: stride must be 1 or 2");
-  }
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM (tcgen05)
@@ -302,9 +254,18 @@ static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool im2col, bool
   const int64_t mb = (M + 127) / 128;
   if (need_even_m_blocks && (mb & 1)) return 0;
   const int64_t pairs = (mb + 1) / 2;
-  const int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 0;
+  int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 0;
   if (bn == 0) return 0;
   if (pairs * (N / bn) < sms / 2) return 0;
+  if (bn == 256) {
+    // wave quantisation: the launch lasts ceil(units / resident pairs) rounds of one tile each, a tile's time scales
+    // with its width.  Few wide tiles can leave most of the last round idle (ResNet-50 stage 5: 98 tiles on 74 pairs =
+    // 2 rounds at 66 %); take 128-column tiles when they shorten the launch by more than 10 %
+    const int64_t slots = sms / 2;
+    const int64_t u256 = pairs * (N / 256), u128 = pairs * (N / 128);
+    const int64_t t256 = (u256 + slots - 1) / slots * 256, t128 = (u128 + slots - 1) / slots * 128;
+    if (t128 * 10 < t256 * 9) bn = 128;
+  }
   return bn;
 }
 
@@ -583,57 +544,6 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   HFR_LAUNCH_CHECK("conv_window");
 }
 
-// ---------------------------------------------------------------------------------------------- fused dw + pw
-bool dwpw_supported(int cin, int cout) {
-  if (cin % 64 || cout % 64) return false;
-  const int bn = cout >= 256 ? 256 : cout;
-  if (cout % bn) return false;
-  const int fixed = bn == 256 ? DwPwSmem<256>::kFixed : bn == 128 ? DwPwSmem<128>::kFixed : DwPwSmem<64>::kFixed;
-  return fixed + (cin / 8) * kDwVecStride * 4 <= 227 * 1024;
-}
-template <int BN>
-static void launch_dwpw_t(const CUtensorMap& tX, const CUtensorMap& tB, const CUtensorMap& tD, const DwPwParams& p,
-                          int device, cudaStream_t s) {
-  static std::atomic<bool> configured[64];
-  if (!configured[device].load()) {
-    cuda_check(cudaFuncSetAttribute(dwpw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-               "cudaFuncSetAttribute(dwpw smem)");
-    configured[device].store(true);
-  }
-  const int grid = p.num_units < device_sm_count(device) ? p.num_units : device_sm_count(device);
-  if (grid < 1) return;
-  launch_pdl(dwpw_kernel<BN>, dim3(grid), dim3(384), (size_t)DwPwSmem<BN>::total(p.Cin), s, tX, tB, tD, p);
-  HFR_LAUNCH_CHECK("dwpw");
-}
-void launch_dwpw(const DwPwArgs& a, int device, cudaStream_t s) {
-  if (!dwpw_supported(a.cin, a.cout)) throw Error(-5, "fused dw+pw: unsupported channel counts");
-  DwPwParams p;
-  memset(&p, 0, sizeof(p));
-  p.Cin = a.cin; p.Cout = a.cout;
-  if (a.H <= 8 && a.W <= 8) { p.tile_n = 2; p.tile_h = 8; } else { p.tile_n = 1; p.tile_h = 16; }
-  p.tiles_x = (a.W + 7) / 8;
-  p.tiles_y = (a.H + p.tile_h - 1) / p.tile_h;
-  p.img_groups = (a.B + p.tile_n - 1) / p.tile_n;
-  p.ww = 10; p.wh = p.tile_h + 2;
-  p.num_kb = a.cin / 64;
-  const int bn = a.cout >= 256 ? 256 : a.cout;
-  p.n_blocks = a.cout / bn;
-  p.num_units = p.img_groups * p.tiles_x * p.tiles_y * p.n_blocks;
-  p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.pw_b = a.pw_b; p.dw_act = a.dw_act; p.pw_act = a.pw_act;
-  const uint64_t xd[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-  const uint64_t xs[3] = {(uint64_t)a.cin * 2, (uint64_t)a.W * a.cin * 2, (uint64_t)a.H * a.W * a.cin * 2};
-  const uint32_t xbox[4] = {64, (uint32_t)p.ww, (uint32_t)p.wh, (uint32_t)p.tile_n};
-  CUtensorMap tX = make_tiled(a.x, PREC_BF16, 4, xd, xs, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
-  CUtensorMap tB = make_tmap_2d(a.pw_w, PREC_BF16, (uint64_t)a.cout, (uint64_t)a.cin, (uint32_t)bn);
-  const uint64_t yd[4] = {(uint64_t)a.cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-  const uint64_t ys[3] = {(uint64_t)a.cout * 2, (uint64_t)a.W * a.cout * 2, (uint64_t)a.H * a.W * a.cout * 2};
-  const uint32_t ybox[4] = {64, 8, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
-  CUtensorMap tD = make_tiled(a.y, PREC_BF16, 4, yd, ys, ybox, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (bn == 256) launch_dwpw_t<256>(tX, tB, tD, p, device, s);
-  else if (bn == 128) launch_dwpw_t<128>(tX, tB, tD, p, device, s);
-  else launch_dwpw_t<64>(tX, tB, tD, p, device, s);
-}
-
 // ---------------------------------------------------------------------------------------------- simple kernels
 
 void launch_maxpool(const PoolArgs& a, int prec, cudaStream_t s) {
@@ -699,6 +609,33 @@ void launch_fc(const float* x, const float* w, const float* bias, float* y, int 
   } else {
     launch_fc_t<32>(x, w, bias, y, B, K, N, act, s);   // 8 k-slices per column: short dependent-load chains
   }
+}
+
+static size_t heads_smem(int K, int n1) {
+  const int slices = kHeadThreads / (n1 / 4);
+  const size_t part = std::max((size_t)slices * kHeadRows * n1, (size_t)4 * kHeadRows * kHeadMaxCols);
+  return ((size_t)kHeadRows * K + part + (size_t)kHeadRows * kHeadMaxHidden + (size_t)kHeadRows * kHeadMaxCols) * sizeof(float);
+}
+bool dense_heads_supported(int K, int n1, int n_heads, const int* n) {
+  if (n1 <= 0 || n1 > kHeadMaxHidden || n1 % 4 || kHeadThreads % (n1 / 4) || n_heads < 0 || n_heads > kHeadMaxHeads) return false;
+  int cols = 0;
+  for (int h = 0; h < n_heads; ++h) cols += n[h];
+  return cols <= kHeadMaxCols && heads_smem(K, n1) <= 200 * 1024;
+}
+void launch_dense_heads(const HeadsArgs& a, cudaStream_t s) {
+  if (!dense_heads_supported(a.K, a.n1, a.n_heads, a.n)) throw Error(-5, "dense heads: unsupported shape");
+  HeadsParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = a.x; p.w1 = a.w1; p.b1 = a.b1; p.hidden = a.hidden; p.B = a.B; p.K = a.K; p.N1 = a.n1; p.act1 = a.act1;
+  p.n_heads = a.n_heads;
+  for (int h = 0; h < a.n_heads; ++h) {
+    p.w[h] = a.w[h]; p.b[h] = a.b[h]; p.y[h] = a.y[h]; p.n[h] = a.n[h]; p.act[h] = a.act[h];
+  }
+  const size_t smem = heads_smem(a.K, a.n1);
+  cuda_check(cudaFuncSetAttribute(dense_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+             "cudaFuncSetAttribute(dense heads smem)");
+  launch_pdl(dense_heads_kernel, dim3((unsigned)((a.B + kHeadRows - 1) / kHeadRows)), dim3(kHeadThreads), smem, s, p);
+  HFR_LAUNCH_CHECK("dense_heads");
 }
 
 void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
@@ -771,10 +708,10 @@ void launch_cast_from_f32(const float* x, void* y, int64_t n, int prec, cudaStre
 }
 
 // ---------------------------------------------------------------------------------------------- 1-NN
-void launch_rows_prep(const float* x, void* xb, float* norms, int64_t n, int d, cudaStream_t s) {
+void launch_rows_prep(const float* x, void* xb, float* norms, float* max_norm, int64_t n, int d, cudaStream_t s) {
   if (n <= 0) return;
   if (d % 4) throw Error(-1, "1-NN: dimension must be a multiple of 4");
-  rows_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(x, (__nv_bfloat16*)xb, norms, (long long)n, d);
+  rows_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(x, (__nv_bfloat16*)xb, norms, max_norm, (long long)n, d);
   HFR_LAUNCH_CHECK("rows_prep");
 }
 
@@ -829,30 +766,41 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
 #undef HFR_KNN_LAUNCH
 }
 
-void launch_knn_finalize_k(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
-                           int64_t nq, int d, int64_t row_offset, int k, float* out_dist, int64_t* out_idx,
-                           cudaStream_t s) {
-  if (nq <= 0) return;
-  if (k < 1 || k > 4) throw Error(-1, "k-NN: k must be 1..4");
-  knn_finalize_k_kernel<8><<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(q, g, part_score, part_idx, splits * 8, (long long)nq, d,
-                                                                    (long long)row_offset, k, out_dist, (long long*)out_idx);
-  HFR_LAUNCH_CHECK("knn_finalize_k");
-}
-
-void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
-                         int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s) {
-  if (nq <= 0) return;
-  knn_finalize_kernel<4><<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(q, g, part_score, part_idx, splits, (long long)nq, d,
-                                                                  (long long)row_offset, best_dist,
-                                                                  (long long*)best_idx);
+void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s) {
+  if (a.nq <= 0) return;
+  if (a.k < 1 || a.k > 4) throw Error(-1, "k-NN: k must be 1..4");
+  KnnFinalizeParams p;
+  p.q = a.q; p.g = a.g; p.part_score = a.part_score; p.part_idx = a.part_idx;
+  p.nbuckets = a.splits * 2;
+  p.nq = a.nq; p.d = a.d; p.row_offset = a.row_offset; p.k = a.k;
+  // rounding bound of the approximate scores (knn.cuh): operands rounded to bf16 (u = 2^-9) or truncated to tf32 by the
+  // MMA (u = 2^-10), fp32 accumulation of d exact products, fp32 norms, the final fma
+  const double u = a.precision == PREC_BF16 ? 1.0 / 512 : 1.0 / 1024;
+  const double c_acc = std::max((double)a.d / 4194304.0, 1.0 / 4096);
+  p.c_dot = 2.0 * (2.0 * u + u * u + c_acc) + 1.0 / 8388608;
+  p.c_norm = (double)(a.d + 4) / 16777216.0;
+  p.gmax2 = a.gmax2;
+  p.out = (Neighbor*)a.out; p.unc_list = a.unc_list; p.counters = a.counters;
+  const unsigned grid = (unsigned)((a.nq + 7) / 8);
+  if (a.cand == 2) knn_finalize_kernel<2, 4><<<grid, 256, 0, s>>>(p);
+  else knn_finalize_kernel<4, 8><<<grid, 256, 0, s>>>(p);
   HFR_LAUNCH_CHECK("knn_finalize");
+  // exact pass over the queries the bound could not certify (usually none: the kernel reads the count and returns)
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnExactSmem)),
+               "cudaFuncSetAttribute(knn exact smem)");
+    configured[device].store(true);
+  }
+  knn_exact_kernel<<<(unsigned)(2 * device_sm_count(device)), 256, sizeof(KnnExactSmem), s>>>(
+      a.q, a.g, (long long)a.n, a.d, (long long)a.row_offset, a.k, a.unc_list, a.counters, a.locks, (Neighbor*)a.out);
+  HFR_LAUNCH_CHECK("knn_exact");
 }
 
-void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
-                      int64_t* best_idx, cudaStream_t s) {
+void launch_knn_merge(const void* parts, int n_parts, int64_t nq, int k, void* out, cudaStream_t s) {
   if (nq <= 0) return;
-  knn_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(dist_all, (const long long*)idx_all, parts,
-                                                                 (long long)nq, best_dist, (long long*)best_idx);
+  knn_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>((const Neighbor*)parts, n_parts, (long long)nq, k,
+                                                                 (Neighbor*)out);
   HFR_LAUNCH_CHECK("knn_merge");
 }
 

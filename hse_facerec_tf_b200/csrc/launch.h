@@ -65,19 +65,6 @@ struct WinArgs {
 bool conv_window_fits(int cin, int kh, int kw);
 void launch_conv_window(const WinArgs& a, int device, cudaStream_t s);
 
-// Fused depthwise 3x3 (stride 1, SAME) + pointwise 1x1 block (dwpw.cuh), bf16.
-struct DwPwArgs {
-  const void* x;        // [B,H,W,cin] bf16
-  const float* dw_w;    // [9][cin]
-  const float* dw_b;    // [cin]
-  const void* pw_w;     // [cout][cin] bf16
-  const float* pw_b;    // [cout] or null
-  void* y;              // [B,H,W,cout] bf16
-  int B, H, W, cin, cout, dw_act, pw_act;
-};
-bool dwpw_supported(int cin, int cout);
-void launch_dwpw(const DwPwArgs& a, int device, cudaStream_t s);
-
 struct DwArgs {
   const void* x;      // [B,H,W,C] of T
   const float* w;     // [9][C]
@@ -121,6 +108,16 @@ void launch_subsample(const void* x, void* y, int B, int H, int W, int C, int Ho
 void launch_gap(const void* x, float* y, int B, int HW, int C, int prec, cudaStream_t s);
 // act: 0 none, 1 relu, 3 sigmoid, 4 softmax
 void launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, cudaStream_t s);
+// The dense tail in one launch: hidden = act1(x W1 + b1) [B, n1], then up to 4 heads head_h = act_h(hidden W_h + b_h).
+// Supported when dense_heads_supported() says so (n1 <= 256 and a multiple of 4, the heads' columns sum to <= 128).
+struct HeadsArgs {
+  const float* x; const float* w1; const float* b1; float* hidden;
+  int B, K, n1, act1, n_heads;
+  const float* w[4]; const float* b[4]; float* y[4];
+  int n[4], act[4];
+};
+bool dense_heads_supported(int K, int n1, int n_heads, const int* n);
+void launch_dense_heads(const HeadsArgs& a, cudaStream_t s);
 // crop + cv2-exact bilinear resize of uint8 RGB boxes: boxes [n][5] = (frame, x1, y1, x2, y2), device int32
 void launch_crop_resize(const uint8_t* frames, int H, int W, const int* boxes, int n, uint8_t* out, int oh, int ow,
                         cudaStream_t s);
@@ -136,7 +133,8 @@ void launch_cast_to_f32(const void* x, float* y, int64_t n, int prec, cudaStream
 void launch_cast_from_f32(const float* x, void* y, int64_t n, int prec, cudaStream_t s);
 
 // 1-NN
-void launch_rows_prep(const float* x, void* x_bf16_or_null, float* norms_or_null, int64_t n, int d, cudaStream_t s);
+void launch_rows_prep(const float* x, void* x_bf16_or_null, float* norms_or_null, float* max_norm_or_null, int64_t n, int d,
+                      cudaStream_t s);
 struct KnnGemmArgs {
   const void* q;  // [nq, d] of T
   const void* g;  // [n, d] of T
@@ -153,18 +151,31 @@ void knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
 // convolution (0: plain 2-D GEMM).
 void gemm_tile_choice(int64_t M, int N, int K, int conv_taps, int sms, int* ctas, int* block_n);
 void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s);
-void launch_knn_finalize(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
-                         int64_t nq, int d, int64_t row_offset, float* best_dist, int64_t* best_idx, cudaStream_t s);
-// k-NN (k <= 4) from 4-candidate partials: out_dist / out_idx are [nq][k], ascending
-void launch_knn_finalize_k(const float* q, const float* g, const float* part_score, const int* part_idx, int splits,
-                           int64_t nq, int d, int64_t row_offset, int k, float* out_dist, int64_t* out_idx,
-                           cudaStream_t s);
+// merge of the candidate records + fp64 re-scoring + certification + (for uncertified queries) the exact fp64 pass;
+// out: device hfr_neighbor [nq][k]
+struct KnnFinalizeArgs {
+  const float* q;
+  const float* g;
+  const float* part_score;
+  const int* part_idx;
+  int splits, cand;
+  int64_t nq, n;
+  int d;
+  int64_t row_offset;
+  int k, precision;
+  const float* gmax2;
+  void* out;
+  int* unc_list;
+  int* counters;
+  int* locks;
+};
+void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s);
 // pairwise euclidean distances (+ optional album age penalty), fp32 direct differences; y == x: the diagonal is forced
 // to exact zeros
 void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,
                           const float* born_x, const float* year_y, const float* born_y, float age_w, float* out,
                           cudaStream_t s);
-void launch_knn_merge(const float* dist_all, const int64_t* idx_all, int parts, int64_t nq, float* best_dist,
-                      int64_t* best_idx, cudaStream_t s);
+// parts: device hfr_neighbor [n_parts][nq][k] -> out [nq][k]
+void launch_knn_merge(const void* parts, int n_parts, int64_t nq, int k, void* out, cudaStream_t s);
 
 }  // namespace hfr

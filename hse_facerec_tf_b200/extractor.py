@@ -50,7 +50,9 @@ class TensorFlowInference:
             w1, h1 = 128, 128
             dw, dh = (orig_w - w1) // 2, (orig_h - h1) // 2
             img = img[dh:-dh, dw:-dw]
-        return _imresize_bilinear(img, (self.w, self.h))
+        # (rows, cols) = (h, w) here and in extract_files.  The reference passes (w, h) to imresize (facerec_test.py:93),
+        # which only works - and is identical - for the square placeholders all of its networks have
+        return _imresize_bilinear(img, (self.h, self.w))
 
     def preprocess_image(self, img_filepath, crop_center):
         """Host restatement of facerec_test.py:80-112 (returns the float array the reference would feed)."""
@@ -113,7 +115,10 @@ class TensorFlowInference:
 
 def extract_keras_features(model, img_filepath, crop_center):
     """facerec_test.py:128-147 with `model` a TensorFlowInference built from the Keras .h5/.pb (caffe-mode
-    preprocess_input == convert2BGR + ImageNet mean).  Keras' load_img resizes with PIL nearest by default."""
+    preprocess_input == convert2BGR + ImageNet mean).  Keras' load_img(target_size=...) resizes with PIL NEAREST
+    (its default interpolation='nearest'); the bare img.resize((w, h)) of the crop_center branch used Pillow's default
+    filter, which was NEAREST in the Pillow releases of the reference's era (it became BICUBIC in Pillow 7): the filter
+    is passed explicitly so the result does not depend on the installed Pillow."""
     from PIL import Image
     w, h = model.w, model.h
     with Image.open(img_filepath) as im:
@@ -123,7 +128,7 @@ def extract_keras_features(model, img_filepath, crop_center):
             im = im.resize((orig_w, orig_h), Image.NEAREST)
             w1, h1 = 128, 128
             dw, dh = (orig_w - w1) / 2, (orig_h - h1) / 2
-            im = im.crop((dw, dh, orig_w - dw, orig_h - dh)).resize((w, h))
+            im = im.crop((dw, dh, orig_w - dw, orig_h - dh)).resize((w, h), Image.NEAREST)
         else:
             im = im.resize((w, h), Image.NEAREST)
         u8 = np.asarray(im)

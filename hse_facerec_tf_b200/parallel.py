@@ -4,7 +4,7 @@
     (B, D) embeddings when one rank needs them all.
   * 1-NN: gallery row-sharded in contiguous blocks; every rank scores all queries against its shard, the per-rank
     (squared distance, global index) pairs are all-gathered (8-12 bytes per query per rank) and merged with
-    lowest-index tie-break by hfr_knn_merge.
+    lowest-index tie-break by hfr_knn_merge (packed {fp64 dist2, int64 index} records, one all_gather_into_tensor).
 
 These helpers only move metadata / small result vectors and work with both the nccl (GPU) and gloo (CPU tests)
 back ends; the compute stays in libhfr.so.
@@ -49,42 +49,45 @@ def shard_layout(n_local: int, y_local, group=None):
     return int(sum(counts[:rank])), np.concatenate(labels), counts
 
 
-def gather_pairs(d2: torch.Tensor, idx: torch.Tensor, group=None):
-    """All-gather per-rank (distance, global index) tensors ([nq] or [nq, k]) -> ([P, ...] float32, [P, ...] int64) on
-    d2's device."""
+def gather_neighbors(rec: torch.Tensor, group=None):
+    """All-gather the packed neighbour records of every rank ([nq, k, 2] int64 = hfr_neighbor {double dist2; int64
+    index}) into [P, nq, k, 2] with ONE collective; the merge is hfr_knn_merge."""
     rank, ws = world(group)
     if ws == 1:
-        return d2.unsqueeze(0), idx.unsqueeze(0)
-    ds = [torch.empty_like(d2) for _ in range(ws)]
-    js = [torch.empty_like(idx) for _ in range(ws)]
-    dist.all_gather(ds, d2.contiguous(), group=group)
-    dist.all_gather(js, idx.contiguous(), group=group)
-    return torch.stack(ds).contiguous(), torch.stack(js).contiguous()
+        return rec.unsqueeze(0)
+    out = torch.empty((ws,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+    if rec.is_cuda:
+        dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    else:                           # gloo (CPU tests): the list form, written straight into the slices of `out`
+        dist.all_gather(list(out.unbind(0)), rec.contiguous(), group=group)
+    return out
 
 
-def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, k: int):
-    """Per-shard k-NN lists gathered as [P, nq, k] -> the global k nearest per query, ascending by (distance, index):
-    [nq, k] float32 / int64.  Shards that returned fewer than k rows pad with (inf, -1), which sort last."""
-    P, nq, kk = d_all.shape
-    d = d_all.permute(1, 0, 2).reshape(nq, P * kk)
-    i = i_all.permute(1, 0, 2).reshape(nq, P * kk)
-    big = torch.iinfo(torch.int64).max
-    order = torch.argsort(torch.where(i < 0, torch.full_like(i, big), i), dim=1, stable=True)   # ties -> lowest index
-    d, i = torch.gather(d, 1, order), torch.gather(i, 1, order)
-    order = torch.argsort(d, dim=1, stable=True)[:, :k]
-    return torch.gather(d, 1, order).contiguous(), torch.gather(i, 1, order).contiguous()
-
-
-def gather_rows(x: torch.Tensor, group=None):
-    """Concatenate per-rank row blocks (possibly of different lengths) in rank order, e.g. (B_r, D) embeddings."""
+def gather_rows(x: torch.Tensor, group=None, total=None):
+    """Concatenate per-rank row blocks (possibly of different lengths) in rank order, e.g. (B_r, D) embeddings.
+    total: number of rows over all ranks when the blocks follow shard_rows(total, world, rank) - then no metadata is
+    exchanged (one all-gather, no host synchronisation); otherwise the counts travel first."""
     rank, ws = world(group)
     if ws == 1:
         return x
-    counts = [None] * ws
-    dist.all_gather_object(counts, int(x.shape[0]), group=group)
+    if total is not None:
+        counts = [shard_rows(total, ws, r)[1] - shard_rows(total, ws, r)[0] for r in range(ws)]
+        if counts[rank] != x.shape[0]:
+            raise ValueError(f"rank {rank} holds {x.shape[0]} rows, shard_rows({total}, {ws}, {rank}) says {counts[rank]}")
+    else:
+        counts = [None] * ws
+        dist.all_gather_object(counts, int(x.shape[0]), group=group)
     m = max(counts)
-    pad = torch.zeros((m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    parts = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(parts, pad, group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    if min(counts) == m:
+        pad = x.contiguous()
+    else:
+        pad = torch.zeros((m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        pad[: x.shape[0]] = x
+    out = torch.empty((ws, m) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if x.is_cuda:
+        dist.all_gather_into_tensor(out, pad, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), pad, group=group)
+    if min(counts) == m:
+        return out.reshape((ws * m,) + tuple(x.shape[1:]))
+    return torch.cat([out[r, :c] for r, c in enumerate(counts)])

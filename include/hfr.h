@@ -192,10 +192,6 @@ int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* b
 int hfr_op_stem_conv_tc(const void* x_u8, const float* w_host, const float* bias, void* y, int batch, int h, int w_,
                         int kh, int kw, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act, int device,
                         void* stream);
-/* Fused MobileNet block: depthwise 3x3 (stride 1, SAME; dw_w [9][cin] fp32, dw_b [cin]) + activation, then pointwise
- * 1x1 (pw_w [cout][cin] bf16, pw_b [cout]) + activation; x, y bf16 NHWC (dwpw.cuh). */
-int hfr_op_dwpw(const void* x, const float* dw_w, const float* dw_b, const void* pw_w, const float* pw_b, void* y,
-                int batch, int h, int w_, int cin, int cout, int dw_act, int pw_act, int device, void* stream);
 /* Stride-1 KHxKW convolution, bf16, cout 32|64, through the smem-window kernel (conv_window.cuh).  w_host: HOST pointer
  * [cout][kh*kw][cin] fp32; synchronises the stream before returning. */
 int hfr_op_conv2d_window(const void* x, const float* w_host, const float* bias, void* y, int batch, int h, int w_,

@@ -86,7 +86,7 @@ def cosine(a, b):
 def merge_pairs_reference(d_all: np.ndarray, i_all: np.ndarray):
     """Test oracle for hfr_knn_merge: per query the smallest distance over the shards, ties -> lowest global index."""
     P, nq = d_all.shape
-    best_d = np.full(nq, np.inf, np.float32)
+    best_d = np.full(nq, np.inf, np.float64)
     best_i = np.full(nq, -1, np.int64)
     for p in range(P):
         for q in range(nq):

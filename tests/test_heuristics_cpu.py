@@ -20,7 +20,7 @@ def tile_choice(m, n, k, taps, sms=148):
 
 
 def test_tile_choice_reproduces_the_profiled_resnet50_step():
-    spec = bench.model_spec("resnet50", "bf16")
+    spec = bench.model_spec("resnet50")
     m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
     layers = m.plan()["layers"]
     names, seen = [], set()

@@ -40,11 +40,13 @@ def _worker(rank, ws, port, out):
         np.testing.assert_array_equal(labels, y)
         nn = neighbors.NearestNeighbors(n_neighbors=1, algorithm="brute").fit(g[a:b])
         d, i = nn.kneighbors(q)
-        d2 = torch.from_numpy((d[:, 0] ** 2).astype(np.float32))
-        gi = torch.from_numpy(i[:, 0].astype(np.int64) + offset)
-        d_all, i_all = parallel.gather_pairs(d2, gi)
-        assert d_all.shape == (ws, len(q))
-        _, best = merge_pairs_reference(d_all.numpy(), i_all.numpy())
+        # the packed hfr_neighbor records {double dist2; int64 index} the GPU path exchanges, [nq, k=1, 2] int64
+        rec = np.zeros((len(q), 1, 2), np.int64)
+        rec[:, 0, 0] = (d[:, 0] ** 2).astype(np.float64).view(np.int64)
+        rec[:, 0, 1] = i[:, 0].astype(np.int64) + offset
+        parts = parallel.gather_neighbors(torch.from_numpy(rec)).numpy()
+        assert parts.shape == (ws, len(q), 1, 2)
+        _, best = merge_pairs_reference(np.ascontiguousarray(parts[:, :, 0, 0]).view(np.float64), parts[:, :, 0, 1])
         emb = parallel.gather_rows(torch.from_numpy(g[a:b]))          # embeddings all-gather with ragged blocks
         assert torch.equal(emb, torch.from_numpy(g))
         mine = parallel.split_batch(np.arange(10))
@@ -82,35 +84,6 @@ def test_shard_rows_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
-
-
-def test_merge_topk_equals_global_knn_with_ties():
-    """parallel.merge_topk over per-shard exact k-NN lists == sklearn's global kneighbors, duplicates included (ties go
-    to the lowest global index), shards smaller than k padded with (inf, -1)."""
-    rs = np.random.RandomState(0)
-    n, nq, d, k = 503, 40, 8, 3
-    g = rs.randn(n, d).astype(np.float32)
-    q = rs.randn(nq, d).astype(np.float32)
-    g[10] = g[400] = g[401]                       # exact duplicates: lowest index first
-    q[0] = g[400]
-    D, I = neighbors.NearestNeighbors(n_neighbors=k, algorithm="brute").fit(g).kneighbors(q)
-    bounds = [0, 2, 120, 400, n]                  # first shard has only 2 rows (< k)
-    dl, il = [], []
-    for a, b in zip(bounds[:-1], bounds[1:]):
-        dd = ((q[:, None, :].astype(np.float64) - g[None, a:b].astype(np.float64)) ** 2).sum(2)
-        o = np.argsort(dd, axis=1, kind="stable")[:, :k]
-        ds, js = np.take_along_axis(dd, o, 1), o + a
-        if b - a < k:
-            ds = np.concatenate([ds, np.full((nq, k - (b - a)), np.inf)], 1)
-            js = np.concatenate([js, np.full((nq, k - (b - a)), -1)], 1)
-        dl.append(ds)
-        il.append(js)
-    d2, idx = parallel.merge_topk(torch.tensor(np.stack(dl), dtype=torch.float32), torch.tensor(np.stack(il)), k)
-    assert idx[0].tolist() == [10, 400, 401]
-    clear = (np.diff(D, axis=1) > 1e-5).all(axis=1)
-    clear[0] = False
-    np.testing.assert_array_equal(idx.numpy()[clear], I[clear])
-    np.testing.assert_allclose(np.sqrt(d2.numpy()[clear]), D[clear], rtol=1e-5)
 
 
 def test_uniform_vote_matches_sklearn_predict():

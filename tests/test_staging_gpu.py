@@ -40,7 +40,7 @@ def test_process_boxes_equals_per_face_reference_path(age_gender_pb, golden_dir)
     frame[50:274, 60:284] = crops[0]
     frame[300:524, 400:624] = crops[2]
     dets = [[70, 60, 274, 264, 0.99], [410, 310, 614, 514, 0.98], [5, 5, 5, 40, 0.3]]
-    fp = hfr.FacialImageProcessing(age_gender_pb, precision="tf32")
+    fp = hfr.FacialImageProcessing(model_file=age_gender_pb, precision="tf32")
     bboxes, ages, genders, feats = fp.process_boxes(frame, dets)
     assert bboxes == [[60, 50, 284, 274], [400, 300, 624, 524]] and len(ages) == 2
     for (x1, y1, x2, y2), a, g, f in zip(bboxes, ages, genders, feats):

@@ -13,6 +13,7 @@
 #   ncu:<w>:<kernel regex>:<skip>:<count>[:tf32]   ncu --set full of matching launches -> prof_<w>_<n>.ncu-rep
 #   mg:<N>           multi-GPU: tests/test_multigpu.py + bench.py under torchrun on N GPUs -> bench_all_n<N>.json
 #   sweep:<N>        tools/sweep.py (config 5) on N GPUs -> sweep_n<N>.json
+#   py:<script>[:arg[:arg]]  any python tool (e.g. py:tools/knn_exactness_report.py)
 #   smoke            __graft_entry__.smoke()
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -73,6 +74,9 @@ for stage in "$@"; do
       [ "$a" = 1 ] && TR=$PY
       timeout -k 5 1500 $TR tools/sweep.py --out gpurun_out/sweep_n$a.json > gpurun_out/sweep_n$a.log 2>&1
       note "sweep n=$a rc=$?";;
+    py)
+      timeout -k 5 1200 $PY $a $b $c > gpurun_out/py_$i.log 2>&1
+      note "py $a rc=$? $(tail -1 gpurun_out/py_$i.log | cut -c1-200)";;
     smoke)
       timeout -k 5 300 $PY -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1
       note "smoke rc=$? $(tail -1 gpurun_out/smoke.log)";;

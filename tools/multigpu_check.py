@@ -32,9 +32,22 @@ def main():
     whole = hfr.KNeighborsClassifier(1, 2, device=dev, precision="bf16").fit(g, y)
     d_w, i_w = whole.kneighbors(q)
     np.testing.assert_array_equal(i_s, i_w)
-    np.testing.assert_allclose(d_s, d_w, rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(d_s, d_w)            # fp64 re-scored distances: identical
     assert i_s[0, 0] == 5
     np.testing.assert_array_equal(sharded.predict(q), whole.predict(q))
+    # queries sharded too (each rank holds the rows it would have extracted): all-gathered over NCCL inside kneighbors
+    qa, qb = parallel.shard_rows(nq, ws, rank)
+    i_lq = sharded.kneighbors(torch.from_numpy(q[qa:qb]).to(dev), return_distance=False, local_queries=True)
+    np.testing.assert_array_equal(i_lq, i_w)
+    # k = 3: per-shard top-3 records, one packed all-gather, merge kernel
+    sh3 = hfr.KNeighborsClassifier(3, 2, device=dev, precision="bf16", sharded=True).fit(g[a:b], y[a:b])
+    wh3 = hfr.KNeighborsClassifier(3, 2, device=dev, precision="bf16").fit(g, y)
+    d3s, i3s = sh3.kneighbors(q)
+    d3w, i3w = wh3.kneighbors(q)
+    np.testing.assert_array_equal(i3s, i3w)
+    np.testing.assert_array_equal(d3s, d3w)
+    assert i3s[0].tolist()[:2] == [5, 40_000]
+    np.testing.assert_array_equal(sh3.predict(q), wh3.predict(q))
     # ---- extraction: batch sharded, no collective on the data path; gather only to compare
     pb = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "age_gender_quantized.pb")
     tfi = hfr.TensorFlowInference(pb, "input_1:0", "global_pooling/Mean:0", device=dev, precision="bf16", input_hw=192)

@@ -15,6 +15,7 @@ from .preprocessing import normalize  # noqa: F401
 from . import parallel  # noqa: F401
 from .decomposition import PCA  # noqa: F401
 from .clustering import album_distance_matrix, pairwise_distances  # noqa: F401
+from .detection import MTCNN  # noqa: F401
 from .staging import crop_resize, expand_and_clamp_boxes, load_resized_batch, resize_pil  # noqa: F401
 
 

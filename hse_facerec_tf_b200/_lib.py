@@ -45,6 +45,10 @@ SIGNATURES = {
     "hfr_knn_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "hfr_knn_debug_candidates": (_i64, [_vp, _vp, _vp, _i64]),
     "hfr_knn_free": (None, [_vp]),
+    "hfr_mtcnn_load": (_i, [_cp, _i, C.POINTER(_vp)]),
+    "hfr_mtcnn_out_shape": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "hfr_mtcnn_run": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hfr_mtcnn_free": (None, [_vp]),
     "hfr_op_dwconv3x3": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "hfr_op_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "hfr_op_stem_conv": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 15 + [_vp]),

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhfr.so")
-CU_SOURCES = ["launch.cu", "api.cu"]
+CU_SOURCES = ["launch.cu", "api.cu", "mtcnn.cu"]
 CC_SOURCES = ["graphdef.cc", "compiler.cc", "h5keras.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall", "--use_fast_math=false"]

@@ -18,6 +18,9 @@
 using namespace hfr;
 
 static thread_local std::string g_err;
+namespace hfr {
+void set_last_error(const std::string& m) { g_err = m; }
+}
 
 template <typename F>
 static int guarded(F&& f) {
@@ -977,7 +980,7 @@ int hfr_pairwise_dist(const float* x, int64_t n, const float* y, int64_t m, int 
     const int given = (year_x != nullptr) + (born_x != nullptr) + (year_y != nullptr) + (born_y != nullptr);
     if (given != 0 && given != 4) throw Error(HFR_ERR_INVALID, "the age penalty needs all of year/born for both sides");
     use_device(device);
-    launch_pairwise_dist(x, y, n, m, dim, year_x, born_x, year_y, born_y, age_weight, out, (cudaStream_t)stream);
+    launch_pairwise_dist(x, y, n, m, dim, year_x, born_x, year_y, born_y, age_weight, out, device, (cudaStream_t)stream);
   });
 }
 
@@ -1182,6 +1185,11 @@ int hfr_op_gemm_bias_act(const void* a_, const void* b, const float* bias, const
                          int n, int k, int act, int dtype, int device, void* stream) {
   return guarded([&] {
     use_device(device);
+    if (dtype == HFR_FP32 && residual == nullptr && k % 4 == 0) {
+      // fp32 operands: the tensor cores at fp32-level accuracy (3xTF32) - the PCA projection of the classifier list
+      launch_gemm_x3((const float*)a_, (const float*)b, bias, (float*)y, m, n, k, n, act, device, (cudaStream_t)stream);
+      return;
+    }
     GemmArgs a;
     a.a = a_; a.b = b; a.bias = bias; a.residual = residual; a.y = y; a.M = m; a.N = n; a.K = k; a.act = act;
     a.round_tf32 = 0;

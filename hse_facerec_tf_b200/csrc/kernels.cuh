@@ -1014,67 +1014,68 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   }
 }
 
-// Pairwise euclidean distance matrix for clustering (scope row 8f-3): out[i,j] = sqrt(sum_k (x[i,k] - y[j,k])^2), the
-// direct form the reference evaluates per pair (process_photos.py:46-48; facial_clustering_test.py:396-400 calls
-// sklearn's pairwise_distances, which upcasts to fp64 - the direct fp32 differences have no cancellation, so both agree
-// to fp32 rounding).  Optional album penalty (process_photos.py:49-52): + w * (a_i - a_j)^2 / (a_i + a_j) with
-// a = max(year_i, year_j) - born, the sum clipped at 0.  64x64 outputs per CTA, 4x4 per thread, K in 16-float slabs.
-__global__ void __launch_bounds__(256) pairwise_dist_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                            long long n, long long m, int d,
-                                                            const float* __restrict__ year_x,
-                                                            const float* __restrict__ born_x,
-                                                            const float* __restrict__ year_y,
-                                                            const float* __restrict__ born_y, float age_w,
-                                                            int zero_diag, float* __restrict__ out) {
-  __shared__ float xs[16][64 + 1], ys[16][64 + 1];
-  const long long i0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread -> rows ty*4.., cols tx*4..
-  float acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (int k0 = 0; k0 < d; k0 += 16) {
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      const int r = e >> 4, k = e & 15;
-      xs[k][r] = (i0 + r < n && k0 + k < d) ? x[(i0 + r) * d + k0 + k] : 0.f;
-      ys[k][r] = (j0 + r < m && k0 + k < d) ? y[(j0 + r) * d + k0 + k] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float xv[4], yv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) xv[a] = xs[k][ty * 4 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) yv[b] = ys[k][tx * 4 + b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const float df = xv[a] - yv[b];
-          acc[a][b] = fmaf(df, df, acc[a][b]);
-        }
-    }
-    __syncthreads();
+// ------------------------------------------------------------------------------------------------------------------
+// fp32-accurate contractions on the tensor cores ("3xTF32"): x = hi + lo with hi = tf32(x), lo = tf32(x - hi) carries 21
+// mantissa bits in two tf32 numbers; a . b ~ hiA.hiB + loA.hiB + hiA.loB (the dropped loA.loB term is 2^-22 relative).
+// The three products are ONE tf32 GEMM over a K dimension three times as long: A' = [hi | lo | hi], B' = [hi | hi | lo].
+// mode 0 writes the A' arrangement, mode 1 the B' arrangement.  out: [rows][3K].
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int K, int mode) {
+  const long long total = rows * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / K;
+    const int k = (int)(i - r * K);
+    const float v = x[i];
+    const float hi = round_tf32(v);
+    const float lo = round_tf32(v - hi);
+    float* o = out + r * 3 * K + k;
+    o[0] = hi;
+    o[K] = mode == 0 ? lo : hi;
+    o[2 * K] = mode == 0 ? hi : lo;
   }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const long long i = i0 + ty * 4 + a;
-    if (i >= n) continue;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const long long j = j0 + tx * 4 + b;
-      if (j >= m) continue;
-      float v = sqrtf(acc[a][b]);
-      if (zero_diag && i == j) v = 0.f;
-      if (year_x != nullptr) {
-        const float my = fmaxf(year_x[i], year_y[j]);
-        const float ai = my - born_x[i], aj = my - born_y[j];
-        v = fmaxf(v + age_w * ((ai - aj) * (ai - aj) / (ai + aj)), 0.f);
+}
+
+// Pairwise euclidean distance matrix for clustering (scope row 8f-3): out[i,j] = sqrt(sum_k (x[i,k] - y[j,k])^2), the
+// expression the reference evaluates per pair (process_photos.py:46-48; facial_clustering_test.py:396-400 calls
+// sklearn's pairwise_distances, which upcasts to fp64).  The cross terms come from the tensor cores (3xTF32 GEMM above,
+// G = X Y^T with fp32-level accuracy); d2 = |x|^2 + |y|^2 - 2 G cancels when the rows are close, so every element whose
+// d2 is below 5 % of |x|^2 + |y|^2 - where the expanded form has lost more than ~1.5 digits - is recomputed from the
+// direct differences (duplicates, the diagonal, near-identical faces: a few elements per row).  Optional album
+// penalty (process_photos.py:49-52): + w * (a_i - a_j)^2 / (a_i + a_j) with a = max(year_i, year_j) - born, clipped at 0.
+__global__ void __launch_bounds__(256) pairwise_post_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ G, int ldg,
+                                                            const float* __restrict__ nx, const float* __restrict__ ny,
+                                                            long long n, long long m, int d,
+                                                            const float* __restrict__ year_x, const float* __restrict__ born_x,
+                                                            const float* __restrict__ year_y, const float* __restrict__ born_y,
+                                                            float age_w, int zero_diag, float* __restrict__ out) {
+  const long long total = n * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / m, j = e - i * m;
+    const float a = nx[i], b = ny[j];
+    // y == x: both (i, j) and (j, i) read the upper-triangle product, so the matrix is exactly symmetric
+    const float gij = (zero_diag && i > j) ? G[j * ldg + i] : G[i * ldg + j];
+    float d2 = a + b - 2.f * gij;
+    if (d2 < 0.05f * (a + b)) {   // cancellation would cost more than ~2 of the 7 digits: direct differences (rare)
+      const float4* xr = reinterpret_cast<const float4*>(x + i * d);
+      const float4* yr = reinterpret_cast<const float4*>(y + j * d);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int k = 0; k < d / 4; ++k) {
+        const float4 p = xr[k], q = yr[k];
+        const float d0 = p.x - q.x, d1 = p.y - q.y, d2_ = p.z - q.z, d3 = p.w - q.w;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2_, d2_, s2); s3 = fmaf(d3, d3, s3);
       }
-      out[i * m + j] = v;
+      d2 = (s0 + s1) + (s2 + s3);
     }
+    float v = sqrtf(fmaxf(d2, 0.f));
+    if (zero_diag && i == j) v = 0.f;
+    if (year_x != nullptr) {
+      const float my = fmaxf(year_x[i], year_y[j]);
+      const float ai = my - born_x[i], aj = my - born_y[j];
+      v = fmaxf(v + age_w * ((ai - aj) * (ai - aj) / (ai + aj)), 0.f);
+    }
+    out[e] = v;
   }
 }
 

@@ -65,6 +65,19 @@ __global__ void __launch_bounds__(256) rows_prep_kernel(const float* __restrict_
   }
 }
 
+// Squared distance of two float32 rows accumulated in fp64 by one warp (lane-strided partial sums, xor-shuffle tree):
+// THE distance every result carries - the certified path and the exact pass both finish with it, so a query's output
+// does not depend on the path it took (nor on how the gallery is sharded).
+__device__ __forceinline__ double warp_dist2_fp64(const float* __restrict__ a, const float* __restrict__ b, int d, int lane) {
+  double acc = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    const double df = (double)a[j] - (double)b[j];
+    acc = fma(df, df, acc);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 struct KnnFinalizeParams {
   const float* q;            // [nq][d] fp32 queries
   const float* g;            // [n][d] fp32 gallery shard
@@ -153,13 +166,7 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const KnnFinalizePara
       ls[KEEP - 1] = INFINITY;
       li[KEEP - 1] = -1;
     }
-    const float* gr = p.g + (long long)hi * p.d;
-    double acc = 0.0;
-    for (int j = lane; j < p.d; j += 32) {
-      const double df = (double)qr[j] - (double)gr[j];
-      acc = fma(df, df, acc);
-    }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double acc = warp_dist2_fp64(qr, p.g + (long long)hi * p.d, p.d, lane);
     // sorted insert into the exact top-4 (ascending distance, ties to the lowest index)
     double cd = acc;
     int ci = hi;
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const KnnFinalizePara
 constexpr int kExQ = 16;        // queries per tile
 constexpr int kExRows = 256;    // gallery rows per iteration (= threads)
 constexpr int kExK = 32;        // k-slab
-constexpr int kExChunk = 2048;  // gallery rows per work item
+// gallery rows per work item: chosen in the kernel from the number of listed queries so that there are ~4 items per CTA
 
 struct KnnExactSmem {
   double qd[kExK][kExQ];            // query slab, converted once
@@ -225,12 +232,14 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
   const int nu = counters[0];
   if (nu == 0) return;
   const int tiles = (nu + kExQ - 1) / kExQ;
-  const long long chunks = (n + kExChunk - 1) / kExChunk;
+  long long chunk_rows = (n * tiles / (4ll * gridDim.x) + kExRows - 1) / kExRows * kExRows;
+  chunk_rows = max((long long)kExRows, min(chunk_rows, 8192ll));
+  const long long chunks = (n + chunk_rows - 1) / chunk_rows;
   const long long items = (long long)tiles * chunks;
   for (long long w = blockIdx.x; w < items; w += gridDim.x) {
     const int tile = (int)(w % tiles);   // CTAs running side by side share a gallery chunk (L2), not a query tile
-    const long long r_begin = (w / tiles) * kExChunk;
-    const long long r_end = min(r_begin + (long long)kExChunk, n);
+    const long long r_begin = (w / tiles) * chunk_rows;
+    const long long r_end = min(r_begin + chunk_rows, n);
     __syncthreads();  // previous item's lists are no longer read
     if (tid < kExQ) {
       const int u = tile * kExQ + tid;
@@ -362,6 +371,43 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
       __threadfence();
       atomicExch(&locks[qr], 0);
     }
+  }
+}
+
+// After the exact pass: the listed queries' neighbours are final as a SET; give them the same distance arithmetic as the
+// certified path (warp_dist2_fp64) and re-sort by (dist2, index).  Warp per listed query.
+__global__ void __launch_bounds__(256) knn_rescore_kernel(const float* __restrict__ q, const float* __restrict__ g, int d,
+                                                           long long row_offset, int k, const int* __restrict__ unc_list,
+                                                           const int* __restrict__ counters, Neighbor* __restrict__ out) {
+  const int nu = counters[0];
+  const int lane = threadIdx.x & 31;
+  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nu; u += gridDim.x * (blockDim.x >> 5)) {
+    const int qr = unc_list[u];
+    Neighbor* o = out + (long long)qr * k;
+    double md[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    long long mi[4] = {-1, -1, -1, -1};
+    for (int e = 0; e < k; ++e) {
+      long long ci = o[e].index;
+      if (ci < 0) continue;
+      double cd = warp_dist2_fp64(q + (long long)qr * d, g + (ci - row_offset) * d, d, lane);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (ci >= 0 && (mi[t] < 0 || cd < md[t] || (cd == md[t] && ci < mi[t]))) {
+          const double td = md[t];
+          const long long ti = mi[t];
+          md[t] = cd;
+          mi[t] = ci;
+          cd = td;
+          ci = ti;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0)
+      for (int t = 0; t < k; ++t) {
+        o[t].dist2 = md[t];
+        o[t].index = mi[t];
+      }
   }
 }
 

@@ -16,6 +16,7 @@ namespace hfr {
 
 static std::atomic<int64_t> g_launches{0};
 int64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
 
 void cuda_check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw Error(-6, std::string(what) + ": " + cudaGetErrorString(e));
@@ -669,15 +670,67 @@ void launch_resize_pil(const uint8_t* images, const long long* desc, int* tab, i
   HFR_LAUNCH_CHECK("resize_pil_bilinear_u8");
 }
 
+void launch_gemm_x3(const float* a, const float* b, const float* bias, float* y, int64_t M, int N, int K, int64_t ldy, int act,
+                    int device, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return;
+  if (K % 4 || ldy < N) throw Error(-1, "gemm x3: K must be a multiple of 4 and ldy >= N");
+  const int Np = (N + 31) / 32 * 32;            // output rows of whole 128-byte lines
+  const int64_t K3 = 3 * (int64_t)K;
+  const int64_t rows_per_pass = std::max<int64_t>(128, (int64_t)(192u << 20) / (K3 * 4));   // <= 192 MB of split A rows
+  const int64_t mp = std::min(M, rows_per_pass);
+  float *a3 = nullptr, *b3 = nullptr, *yt = nullptr, *biasp = nullptr;
+  cuda_check(cudaMallocAsync((void**)&a3, (size_t)mp * K3 * 4, s), "cudaMallocAsync(x3 A)");
+  cuda_check(cudaMallocAsync((void**)&b3, (size_t)Np * K3 * 4, s), "cudaMallocAsync(x3 B)");
+  cuda_check(cudaMallocAsync((void**)&yt, (size_t)mp * Np * 4, s), "cudaMallocAsync(x3 Y)");
+  cuda_check(cudaMemsetAsync(b3, 0, (size_t)Np * K3 * 4, s), "cudaMemsetAsync");
+  split_tf32_kernel<<<grid_for((long long)N * K, 256), 256, 0, s>>>(b, b3, (long long)N, K, 1);
+  HFR_LAUNCH_CHECK("split_tf32");
+  if (bias && Np != N) {   // the epilogue reads Np bias values
+    cuda_check(cudaMallocAsync((void**)&biasp, (size_t)Np * 4, s), "cudaMallocAsync(x3 bias)");
+    cuda_check(cudaMemsetAsync(biasp, 0, (size_t)Np * 4, s), "cudaMemsetAsync");
+    cuda_check(cudaMemcpyAsync(biasp, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync(bias)");
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += mp) {
+    const int64_t mm = std::min(mp, M - m0);
+    split_tf32_kernel<<<grid_for((long long)mm * K, 256), 256, 0, s>>>(a + m0 * K, a3, (long long)mm, K, 0);
+    HFR_LAUNCH_CHECK("split_tf32");
+    GemmArgs g;
+    g.a = a3; g.b = b3; g.bias = biasp ? biasp : bias; g.residual = nullptr; g.y = yt; g.M = mm; g.N = Np; g.K = (int)K3;
+    g.act = act; g.round_tf32 = 0;
+    launch_gemm(g, PREC_TF32, device, s);
+    cuda_check(cudaMemcpy2DAsync(y + m0 * ldy, (size_t)ldy * 4, yt, (size_t)Np * 4, (size_t)N * 4, (size_t)mm,
+                                 cudaMemcpyDeviceToDevice, s), "cudaMemcpy2DAsync(x3 out)");
+  }
+  if (biasp) cuda_check(cudaFreeAsync(biasp, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(yt, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(b3, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(a3, s), "cudaFreeAsync");
+}
+
 void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,
                           const float* born_x, const float* year_y, const float* born_y, float age_w, float* out,
-                          cudaStream_t s) {
+                          int device, cudaStream_t s) {
   if (n <= 0 || m <= 0) return;
-  const int64_t gy = (n + 63) / 64, gx = (m + 63) / 64;
-  if (gy > 65535) throw Error(-1, "pairwise distances: too many rows for one launch");
-  pairwise_dist_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(x, y, (long long)n, (long long)m, d, year_x, born_x,
-                                                                         year_y, born_y, age_w, x == y ? 1 : 0, out);
-  HFR_LAUNCH_CHECK("pairwise_dist");
+  if (d % 4) throw Error(-1, "pairwise distances: the dimension must be a multiple of 4");
+  // cross terms G = X Y^T on the tensor cores (3xTF32), norms in fp32, then d2 = |x|^2 + |y|^2 - 2 G with the
+  // cancelling elements recomputed directly (pairwise_post_kernel)
+  const int64_t mpad = (m + 31) / 32 * 32;
+  float *G = nullptr, *nx = nullptr, *ny = nullptr;
+  cuda_check(cudaMallocAsync((void**)&G, (size_t)n * mpad * 4, s), "cudaMallocAsync(pairwise G)");
+  cuda_check(cudaMallocAsync((void**)&nx, (size_t)n * 4, s), "cudaMallocAsync(norms)");
+  launch_rows_prep(x, nullptr, nx, nullptr, n, d, s);
+  if (y != x) {
+    cuda_check(cudaMallocAsync((void**)&ny, (size_t)m * 4, s), "cudaMallocAsync(norms)");
+    launch_rows_prep(y, nullptr, ny, nullptr, m, d, s);
+  }
+  launch_gemm_x3(x, y, nullptr, G, n, (int)m, d, mpad, 0, device, s);
+  pairwise_post_kernel<<<grid_for((long long)n * m, 256), 256, 0, s>>>(x, y, G, (int)mpad, nx, ny ? ny : nx, (long long)n,
+                                                                        (long long)m, d, year_x, born_x, year_y, born_y,
+                                                                        age_w, x == y ? 1 : 0, out);
+  HFR_LAUNCH_CHECK("pairwise_post");
+  if (ny) cuda_check(cudaFreeAsync(ny, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(nx, s), "cudaFreeAsync");
+  cuda_check(cudaFreeAsync(G, s), "cudaFreeAsync");
 }
 
 void launch_age_post(const float* probs, float* age, int B, int N, cudaStream_t s) {
@@ -795,6 +848,8 @@ void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s) {
   knn_exact_kernel<<<(unsigned)(2 * device_sm_count(device)), 256, sizeof(KnnExactSmem), s>>>(
       a.q, a.g, (long long)a.n, a.d, (long long)a.row_offset, a.k, a.unc_list, a.counters, a.locks, (Neighbor*)a.out);
   HFR_LAUNCH_CHECK("knn_exact");
+  knn_rescore_kernel<<<64, 256, 0, s>>>(a.q, a.g, a.d, (long long)a.row_offset, a.k, a.unc_list, a.counters, (Neighbor*)a.out);
+  HFR_LAUNCH_CHECK("knn_rescore");
 }
 
 void launch_knn_merge(const void* parts, int n_parts, int64_t nq, int k, void* out, cudaStream_t s) {

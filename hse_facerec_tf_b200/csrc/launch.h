@@ -21,6 +21,8 @@ inline size_t elt_size(int prec) { return prec == PREC_BF16 ? 2 : 4; }
 int device_sm_count(int device);
 void use_device(int device);  // cudaSetDevice + sm_100 check
 int64_t launch_count();
+void count_launch();                         // for kernels launched outside launch.cu (mtcnn.cu)
+void set_last_error(const std::string& m);   // thread-local message behind hfr_last_error() (defined in api.cu)
 
 struct StemArgs {
   const void* x;  // [B,H,W,3] u8 or f32
@@ -85,6 +87,10 @@ struct GemmArgs {
   int act, round_tf32;
 };
 void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s);
+// fp32-accurate y[M, N] = act(a[M,K] b[N,K]^T + bias) on the tensor cores (3xTF32, kernels.cuh); ldy >= N is y's row
+// pitch in floats.  Needs K % 4 == 0; scratch comes from the stream-ordered allocator.
+void launch_gemm_x3(const float* a, const float* b, const float* bias, float* y, int64_t M, int N, int K, int64_t ldy, int act,
+                    int device, cudaStream_t s);
 
 struct ConvArgs {  // KxK convolution as implicit GEMM (NHWC), weights [cout][kh*kw][cin]
   const void* x;
@@ -174,7 +180,7 @@ void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s);
 // to exact zeros
 void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,
                           const float* born_x, const float* year_y, const float* born_y, float age_w, float* out,
-                          cudaStream_t s);
+                          int device, cudaStream_t s);
 // parts: device hfr_neighbor [n_parts][nq][k] -> out [nq][k]
 void launch_knn_merge(const void* parts, int n_parts, int64_t nq, int k, void* out, cudaStream_t s);
 

@@ -176,6 +176,23 @@ int hfr_knn_stats(hfr_knn* k, int64_t* certified, int64_t* rescored);
 int64_t hfr_knn_debug_candidates(hfr_knn* k, float* score_host, int32_t* index_host, int64_t nq);
 void hfr_knn_free(hfr_knn* k);
 
+/* ---- MTCNN face detector networks (scope row 8f-4) -------------------------------------------------------------------
+ * Replaces the three sess.run lambdas of FacialImageProcessing.load_mtcnn (facial_analysis.py:334-352) over the
+ * reference's mtcnn.pb; the cascade around them (image pyramid, NMS, box regression: facial_analysis.py:354-604) is host
+ * code.  net: 0 = P-Net (any h x w), 1 = R-Net (24 x 24), 2 = O-Net (48 x 48).  x: device float32 [n, h, w, 3] exactly as
+ * the reference feeds the placeholder ((pixel - 127.5) * 0.0078125, width-major as mtcnn_detect_faces transposes it).
+ * Outputs (device float32, slots in the order load_mtcnn binds them):
+ *   P-Net  out0 = pnet/conv4-2/BiasAdd [n, ho, wo, 4]   out1 = pnet/prob1 [n, ho, wo, 2]
+ *   R-Net  out0 = rnet/conv5-2 [n, 4]                   out1 = rnet/prob1 [n, 2]
+ *   O-Net  out0 = onet/conv6-2 [n, 4]   out1 = onet/conv6-3 [n, 10]   out2 = onet/prob1 [n, 2]
+ * hfr_mtcnn_out_shape gives (ho, wo, channels) of an output slot for an input size. */
+typedef struct hfr_mtcnn hfr_mtcnn;
+int hfr_mtcnn_load(const char* mtcnn_pb_path, int device, hfr_mtcnn** out);
+int hfr_mtcnn_out_shape(const hfr_mtcnn* m, int net, int h, int w, int slot, int* oh, int* ow, int* oc);
+int hfr_mtcnn_run(hfr_mtcnn* m, int net, const float* x, int n, int h, int w, float* out0, float* out1, float* out2,
+                  void* stream);
+void hfr_mtcnn_free(hfr_mtcnn* m);
+
 /* ---- single operators (kernel-level parity tests and profiling) ---------------------------------------------------
  * dtype: HFR_FP32/HFR_TF32 -> float32 tensors, HFR_BF16 -> bfloat16 tensors.  act: 0 none, 1 relu, 2 relu6. */
 int hfr_op_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int batch, int h, int w, int c,

@@ -202,6 +202,14 @@ class GraphOracle:
             return torch.rsqrt(args[0])
         if op == "Sqrt":
             return torch.sqrt(args[0])
+        if op == "Neg":
+            return -args[0]
+        if op == "Exp":
+            return torch.exp(args[0])
+        if op in ("Max", "Sum"):       # reductions of the hand-spelled softmax in mtcnn.pb (Max -> Sub -> Exp -> Sum -> RealDiv)
+            axes = [int(a) for a in np.asarray(args[1]).reshape(-1)]
+            keep = bool(nd.attrs.get("keep_dims", False))
+            return args[0].amax(dim=axes, keepdim=keep) if op == "Max" else args[0].sum(dim=axes, keepdim=keep)
         if op == "Relu":
             return torch.relu(args[0])
         if op == "Relu6":

@@ -9,6 +9,8 @@ Outputs
                             /root/reference, so the model the library is a drop-in for must travel with the tests.
   face_crops_u8.npz         RGB uint8 crops of age_gender_identity/test_image.jpg resized with cv2.resize
                             (INTER_LINEAR, as facial_analysis.py:95) to 224 and 192, plus shifted/flipped variants.
+  mtcnn.pb, test_image.jpg  byte copies of age_gender_identity/mtcnn.pb (the detector's weights, the file the MTCNN drop-in
+                            exists to load) and of the demo photo the notebook runs on - inputs of the detector tests.
   kat_oracle.npz            oracle outputs (f32-dequant, fp32 compute) for zeros / seeded noise / crops at 224 and
                             192 - lets the GPU tests check against values produced in THIS container as well.
 """
@@ -29,6 +31,11 @@ PB = os.path.join(REF, "age_gender_tf2_new-01-0.14-0.92_quantized.pb")
 SHA = "2a917c62e3a6cdd2d1556a86ae564dacb3704243048659d5d4d217933239dee3"
 
 
+def copy_detector_fixtures():
+    for name in ("mtcnn.pb", "test_image.jpg"):
+        shutil.copyfile(os.path.join(REF, name), os.path.join(HERE, name))
+
+
 def crops(size):
     img = cv2.cvtColor(cv2.imread(os.path.join(REF, "test_image.jpg")), cv2.COLOR_BGR2RGB)
     boxes = [(203, 285, 581, 663), (195, 290, 570, 670), (210, 280, 590, 655), (150, 330, 520, 720)]
@@ -47,6 +54,7 @@ def main():
     data = open(PB, "rb").read()
     assert hashlib.sha256(data).hexdigest() == SHA
     shutil.copyfile(PB, os.path.join(HERE, "age_gender_quantized.pb"))
+    copy_detector_fixtures()
     c224, c192 = crops(224), crops(192)
     np.savez_compressed(os.path.join(HERE, "face_crops_u8.npz"), c224=c224, c192=c192)
 

@@ -24,7 +24,7 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
     m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
     layers = m.plan()["layers"]
     names, seen = [], set()
-    with open(os.path.join(ROOT, "profiles", "r1_resnet50_launches.csv")) as f:
+    with open(os.path.join(ROOT, "profiles", "r2_resnet50_launches.csv")) as f:
         for r in csv.DictReader(l for l in f if not l.startswith("==")):
             if r["ID"] not in seen:
                 seen.add(r["ID"])

@@ -33,14 +33,14 @@ def main():
     for precision in ("bf16", "tf32"):
         for n, nq, d, kind in ((1_000_000, 20_000, 1024, "random"), (100_000, 20_000, 2048, "random"),
                                (1_000_000, 20_000, 1024, "planted sigma=0.05")):
-            rs = np.random.RandomState(n % 1000 + d)
-            g = rs.standard_normal((n, d), dtype=np.float32)
-            g /= np.linalg.norm(g, axis=1, keepdims=True)
+            gen = torch.Generator().manual_seed(n % 1000 + d)
+            g = torch.randn(n, d, generator=gen)
+            g = (g / g.norm(dim=1, keepdim=True)).numpy()
             if kind == "random":
-                q = rs.standard_normal((nq, d), dtype=np.float32)
+                q = torch.randn(nq, d, generator=gen)
             else:
-                q = g[rs.randint(0, n, nq)] + 0.05 * rs.standard_normal((nq, d), dtype=np.float32)
-            q /= np.linalg.norm(q, axis=1, keepdims=True)
+                q = torch.from_numpy(g[torch.randint(0, n, (nq,), generator=gen).numpy()]) + 0.05 * torch.randn(nq, d, generator=gen)
+            q = (q / q.norm(dim=1, keepdim=True)).numpy()
             clf = hfr.KNeighborsClassifier(precision=precision).fit(torch.from_numpy(g).cuda(), np.arange(n))
             qd = torch.from_numpy(q).cuda()
             clf.kneighbors(qd)

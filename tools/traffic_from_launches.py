@@ -1,5 +1,5 @@
 """profiles/traffic_<workload>.json from an ncu launch list (gpu time + dram bytes per launch), one bench step.
-usage: python tools/traffic_from_launches.py <launches.csv> <workload> <launches per step>"""
+usage: python tools/traffic_from_launches.py <launches.csv> <workload> <launches per step> [steps to skip]"""
 import collections
 import csv
 import json
@@ -21,7 +21,7 @@ def kernel_class(name):
     if "conv_window_kernel<4" in name.replace(" ", ""):
         return "stem"
     for key, cls in (("conv_window", "conv"), ("stem_s2d", "stem"), ("stem_conv", "stem"), ("dwconv3x3", "dw"), ("dwpw", "dwpw"),
-                     ("maxpool", "maxpool"), ("subsample", "subsample"), ("gap_kernel", "gap"), ("fc_kernel", "fc")):
+                     ("maxpool", "maxpool"), ("subsample", "subsample"), ("gap_kernel", "gap"), ("fc_kernel", "fc"), ("dense_heads", "fc")):
         if key in name:
             return cls
     return "other"
@@ -34,7 +34,7 @@ def plan_classes(workload):
     sys.path.insert(0, ROOT)
     import bench
     import hse_facerec_tf_b200 as hfr
-    spec = bench.model_spec(workload, "bf16")
+    spec = bench.model_spec(workload)
     m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
     layers = m.plan()["layers"]
     seq = []
@@ -49,12 +49,13 @@ def plan_classes(workload):
 
 def main():
     path, workload, per_step = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     lines = [l for l in open(path) if not l.startswith("==")]
     by = collections.OrderedDict()
     for r in csv.DictReader(lines):
         d = by.setdefault(r["ID"], {"name": r["Kernel Name"]})
         d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
-    launches = list(by.values())[:per_step]
+    launches = list(by.values())[skip * per_step:(skip + 1) * per_step]
     try:
         seq = plan_classes(workload)
     except Exception as e:  # noqa: BLE001

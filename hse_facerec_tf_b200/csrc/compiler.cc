@@ -371,6 +371,10 @@ struct Lowerer {
       const AttrVal* ea = n.attr("epsilon");
       const float eps = ea ? ea->f : 1e-3f;
       const int C = vals[a[0].vid].C;
+      for (int i = 1; i < 5; ++i)   // untrusted file: the four parameter vectors must be constants of C elements
+        if (a[(size_t)i].k != Sym::CONST || !a[(size_t)i].c || (int64_t)a[(size_t)i].c->f.size() < C)
+          fail("FusedBatchNorm '" + n.name + "': scale / offset / mean / variance must be constant vectors of " +
+               std::to_string(C) + " elements");
       HTensor sc, sh;
       sc.shape = sh.shape = {C};
       sc.f.resize((size_t)C);
@@ -405,6 +409,7 @@ struct Lowerer {
       if (df && df->s != "NHWC") fail(op + " '" + n.name + "': only NHWC is supported");
       const HTensor& w = *a[1].c;
       if (w.shape.size() != 4) fail(op + " '" + n.name + "': kernel must be rank 4");
+      if ((int64_t)w.f.size() != w.numel() || w.numel() <= 0) fail(op + " '" + n.name + "': kernel data does not match its shape");
       IOp o;
       o.kind = op == "Conv2D" ? IOp::CONV : IOp::DWCONV;
       o.name = n.name;
@@ -502,6 +507,7 @@ struct Lowerer {
       if (ta && ta->b) fail("MatMul '" + n.name + "': transpose_a is not supported");
       auto w = std::make_shared<HTensor>(*a[1].c);
       if (w->shape.size() != 2) fail("MatMul '" + n.name + "': weight must be rank 2");
+      if ((int64_t)w->f.size() != w->numel() || w->numel() <= 0) fail("MatMul '" + n.name + "': weight data does not match its shape");
       if (tb && tb->b) {
         HTensor t = *w;
         int64_t R = t.shape[0], Cc = t.shape[1];

@@ -37,6 +37,7 @@ struct WinParams {
                                     // exactly 8 pixels wide -> every 8-row operand group is one aligned 128-byte line
   int copy_pitch;                   // bytes between consecutive shifted copies
   int round_tf32;                   // fp32 output only: round to tf32 (the consumer is a tf32 tensor-core layer)
+  int stages;                       // window ring depth (kWinStagesMin .. kWinStagesMax)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -55,9 +56,12 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
   return d;
 }
 
-constexpr int kWinStages = 3;
+// Window ring depth: a slot is recycled only after the MMAs that read it have completed, so the depth must cover the
+// load latency (ncu r2: with 3 slots the stem sat at 0.94 us per tile - (load latency + MMA time) / 3 - against 0.41 us
+// of MMA work).  The launcher takes as many slots as fit next to the resident weights, between these bounds.
+constexpr int kWinStagesMin = 3, kWinStagesMax = 6;
 
-// dynamic smem: [1 KB align][weights w_bytes][kWinStages x window win_bytes (1 KB-rounded)][4 x 16 KB staging][barriers]
+// dynamic smem: [1 KB align][weights w_bytes][p.stages x window win_bytes (1 KB-rounded)][4 x 16 KB staging][barriers]
 // TH x TW taps with KS K=16 steps each known at compile time unroll the MMA issue completely (TH = 0: runtime loops).
 // TOut = float (experimental, the tf32-mode stem): fp32 output in two 32-column chunks per tile.  PASSES = 2: the weight
 // matrix holds a second copy of every tap with the bf16 residual of the weights (w = hi + lo, 16 mantissa bits), issued
@@ -73,14 +77,15 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sW = smem_base;
   const uint32_t sWin = sW + w_bytes;                      // w_bytes is a multiple of 1024
+  const int kWinStages = p.stages;
   const uint32_t sEpi = sWin + kWinStages * win_stride;    // win_stride is a multiple of 1024
   const uint32_t sBar = sEpi + 4 * 16384;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (sBar - smem_base) + 192);
-  auto full_bar = [&](int s) { return sBar + 8u * s; };
-  auto empty_bar = [&](int s) { return sBar + 32u + 8u * s; };
-  auto tfull_bar = [&](int s) { return sBar + 64u + 8u * s; };
-  auto tempty_bar = [&](int s) { return sBar + 80u + 8u * s; };
-  const uint32_t wfull_bar = sBar + 96u;
+  auto full_bar = [&](int s) { return sBar + 8u * s; };            // up to kWinStagesMax = 6 slots: 48 bytes each kind
+  auto empty_bar = [&](int s) { return sBar + 48u + 8u * s; };
+  auto tfull_bar = [&](int s) { return sBar + 96u + 8u * s; };
+  auto tempty_bar = [&](int s) { return sBar + 112u + 8u * s; };
+  const uint32_t wfull_bar = sBar + 128u;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;

@@ -4,8 +4,7 @@
 //   warp 1           MMA issuer:   tcgen05.mma, M=128 x N=BLOCK_N per CTA, fp32 accumulators in TMEM (2 stages)
 //   warp 2           TMEM allocator
 //   warps 4..11      epilogue:     two warpgroups ping-pong on tiles (accumulator stage g = tile & 1);
-//                                  tcgen05.ld -> registers -> fused epilogue (residual rows: 16-byte global loads
-//                                  into registers, requested two 128-byte chunks ahead)
+//                                  tcgen05.ld -> registers -> fused epilogue
 //   The producer and issuer warps run their loops whole-warp in uniform control flow; one elected lane issues
 //   (elect_one() in ptx.cuh explains why that matters for the issue rate).
 //
@@ -110,6 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return sBar + 64u + 8u * s; };
   auto tfull_bar = [&](int s) { return sBar + 128u + 8u * s; };
   auto tempty_bar = [&](int s) { return sBar + 144u + 8u * s; };
+  auto rfull_bar = [&](int s) { return sBar + 160u + 8u * s; };  // residual tile landed in staging buffer s (0..3)
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -122,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmD);
+    if (EPI == EPI_STORE && p.residual != nullptr) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -130,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
+    for (int s = 0; s < 4; ++s) mbar_init(rfull_bar(s), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS, CTAS>(smem_u32(tmem_slot));
@@ -317,35 +319,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int NCHUNK = BLOCK_N / CH_ELEMS;
       uint32_t chunk_ctr = 0;
       const bool use_res = (p.residual != nullptr);
-      // Residual rows come straight from global memory into registers: thread `row` owns 128 contiguous bytes per
-      // chunk (one full line), two chunks in flight.  The first two chunks of a tile are requested BEFORE the wait for
-      // the tile's accumulator, so their latency hides behind the mainloop; chunk c + 2 is requested while chunk c is
-      // being finished.  (A TMA prefetch one chunk ahead into the staging buffer left the epilogue latency-bound on
-      // the load: ~2 us per 128x128 tile on the short-K "increase" layers, ncu r2.)
-      const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
-      const size_t res_pitch = (size_t)p.N * sizeof(T);
-      uint4 rcur[8], rnxt[8];   // residual of the chunk being finished / of the next one
-      auto res_load = [&](int mb2, int n2, uint4 (&dst)[8]) {
-        const int m2 = mb2 * 128 + row;
-        if (m2 < p.M && n2 < p.N) {
-          const uint4* src = reinterpret_cast<const uint4*>(res_base + (size_t)m2 * res_pitch + (size_t)n2 * sizeof(T));
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = ld_global_nc_v4(src + q);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+      // Residual tiles travel by TMA into the staging buffer the output chunk will be written to (same swizzled
+      // layout, updated in place), prefetched one chunk ahead by the warpgroup leader.
+      const int units_n2 = (p.num_n_blocks + p.n_blocks_per_unit - 1) / p.n_blocks_per_unit;
+      int pf_t = g, pf_c = 0;           // leader only: next (local tile, chunk) whose residual has not been requested
+      uint32_t pf_ctr = 0;
+      auto prefetch_next = [&]() {      // leader only
+        const int u2 = unit0 + pf_t * unit_stride;
+        if (u2 >= p.num_units) return;
+        const int mb2 = (u2 / units_n2) * CTAS + (int)cta_rank, nb2 = u2 % units_n2;
+        const int n2 = nb2 * BLOCK_N + pf_c * CH_ELEMS;
+        const uint32_t b2 = pf_ctr & 1;
+        mbar_expect_tx(rfull_bar(g * 2 + b2), 16384);
+        tma_load_2d(sEpi + (g * 2 + b2) * 16384, &tmR, rfull_bar(g * 2 + b2), n2, mb2 * 128);
+        ++pf_ctr;
+        if (++pf_c == NCHUNK || nb2 * BLOCK_N + pf_c * CH_ELEMS >= p.N) {
+          pf_c = 0;
+          pf_t += 2;
         }
       };
+      if (use_res && leader) prefetch_next();
       for (int u = unit0; u < p.num_units; u += unit_stride, ++tile) {
         if ((tile & 1) != (uint32_t)g) continue;
         int mb, nb0, nbn;
         decode(u, mb, nb0, nbn);
         const uint32_t aphase = my_tiles & 1;
         ++my_tiles;
-        if (use_res) {
-          res_load(mb, nb0 * BLOCK_N, rcur);
-          if (NCHUNK > 1) res_load(mb, nb0 * BLOCK_N + CH_ELEMS, rnxt);
-        }
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
@@ -353,9 +352,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n0 >= p.N) break;  // uniform across the CTA
           const uint32_t buf = chunk_ctr & 1;
           const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
-          // the TMA store that last read this staging buffer must have finished reading it
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(bar_id, 128);
+          uint4 rv[8];
+          if (use_res) {
+            if (leader) {
+              tma_store_wait_read<0>();  // the other buffer's last store has finished reading it ...
+              prefetch_next();           // ... so the next chunk's residual may land there
+            }
+            mbar_wait(rfull_bar(g * 2 + buf), (chunk_ctr >> 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t a = st_row + (((uint32_t)q ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rv[q].x), "=r"(rv[q].y), "=r"(rv[q].z), "=r"(rv[q].w)
+                           : "r"(a));
+            }
+          } else {
+            // the TMA store that last read this staging buffer must have finished reading it
+            if (leader) tma_store_wait_read<1>();
+            named_bar_sync(bar_id, 128);
+          }
 #pragma unroll
           for (int h = 0; h < CH_ELEMS / 32; ++h) {
             uint32_t r[32];
@@ -380,15 +395,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if constexpr (sizeof(T) == 4) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  v[4 * q] += __uint_as_float(rcur[q].x);
-                  v[4 * q + 1] += __uint_as_float(rcur[q].y);
-                  v[4 * q + 2] += __uint_as_float(rcur[q].z);
-                  v[4 * q + 3] += __uint_as_float(rcur[q].w);
+                  v[4 * q] += __uint_as_float(rv[q].x);
+                  v[4 * q + 1] += __uint_as_float(rv[q].y);
+                  v[4 * q + 2] += __uint_as_float(rv[q].z);
+                  v[4 * q + 3] += __uint_as_float(rv[q].w);
                 }
               } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const uint4 t = rcur[h * 4 + q];
+                  const uint4 t = rv[h * 4 + q];
                   const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -427,11 +442,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              "r"(w[3]));
               }
             }
-          }
-          if (use_res && NCHUNK > 1) {   // roll the window: next chunk becomes current, chunk c + 2 is requested
-#pragma unroll
-            for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
-            if (c + 2 < NCHUNK) res_load(mb, n0 + 2 * CH_ELEMS, rnxt);
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);

@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(16 * VL + 32) dwconv3x3_pipe_kernel(const __gr
             const int kr = r - o * STRIDE;  // filter row this input row hits for output o
             if (kr >= 0 && kr < 3) {
 #pragma unroll
-              for (int e = 0; e < VN; ++e) acc[o][e] = fmaf(xv[e], wk[kr][e], acc[o][e]);
+              for (int e = 0; e < VN; e += 2)   // packed fp32 FMA: same rounding as fmaf, half the issue slots
+                ffma2(acc[o][e], acc[o][e + 1], xv[e], xv[e + 1], wk[kr][e], wk[kr][e + 1]);
             }
           }
         }

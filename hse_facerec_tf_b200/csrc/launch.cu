@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "conv_window.cuh"
+#include "gemm_chain.cuh"
 #include "kernels.cuh"
 
 namespace hfr {
@@ -346,6 +347,77 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
   else launch_gemm_store<float, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
 }
 
+// ---------------------------------------------------------------------------------------------- chained GEMM pair
+static int chain_mode() {   // HFR_CHAIN=0: never; unset / 1: pairs whose layers both run as 1-CTA tiles; 2: every eligible pair
+  const char* e = getenv("HFR_CHAIN");   // read per call (host-side, once per launch): tests flip it between models
+  return e ? atoi(e) : 1;
+}
+bool gemm_chain_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int device) {
+  if (chain_mode() == 0 || prec == PREC_FP32) return false;
+  const int es = (int)elt_size(prec);
+  if (a.M != b.M || b.a != a.y || a.N != b.K || a.M <= 0 || a.M >= (1ll << 31)) return false;
+  if ((a.K * es) % 16 || (b.K * es) % 16 || (a.N * es) % 128 || (b.N * es) % 128) return false;
+  if (a.N % 128) return false;                       // the producer's tiles are whole 128-column blocks
+  const int sms = device_sm_count(device);
+  if ((a.M + 127) / 128 < 4 * sms) return false;     // short launches: nothing to overlap, the lag would cover the whole problem
+  if (chain_mode() == 1) {
+    int ctas, bn;
+    gemm_tile_choice(a.M, a.N, a.K, 0, sms, &ctas, &bn);
+    if (ctas != 1) return false;
+    gemm_tile_choice(b.M, b.N, b.K, 0, sms, &ctas, &bn);
+    if (ctas != 1) return false;
+  }
+  return true;
+}
+
+template <typename T>
+static void launch_gemm_chain_t(const GemmArgs& a, const GemmArgs& b, int prec, int device, unsigned* done, cudaStream_t s) {
+  constexpr int BN = 128;
+  using SM = GemmSmem<BN, EPI_STORE, 1>;
+  auto kern = gemm_chain_kernel<T, BN>;
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal),
+               "cudaFuncSetAttribute(gemm chain smem)");
+    configured[device].store(true);
+  }
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  const GemmArgs* g[2] = {&a, &b};
+  for (int q = 0; q < 2; ++q) {
+    p.pr[q].N = g[q]->N; p.pr[q].K = g[q]->K; p.pr[q].num_n_blocks = (g[q]->N + BN - 1) / BN;
+    p.pr[q].bias = g[q]->bias; p.pr[q].residual = g[q]->residual; p.pr[q].act = g[q]->act; p.pr[q].round_tf32 = g[q]->round_tf32;
+  }
+  p.M = (int)a.M;
+  p.num_m_blocks = (int)((a.M + 127) / 128);
+  const int G = p.pr[0].num_n_blocks + p.pr[1].num_n_blocks;
+  const int grid = device_sm_count(device);
+  p.lag = (6 * grid + G - 1) / G + 1;                // the consumer trails by ~6 waves of units (>= 4 is required, see the
+                                                     // kernel header): its rows are published by then and still in L2
+  p.num_units = (p.num_m_blocks + p.lag) * G;
+  p.done = done;
+  CUtensorMap tA0 = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
+  CUtensorMap tB0 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, BN);
+  CUtensorMap tD0 = make_tmap_2d(a.y, prec, (uint64_t)a.M, (uint64_t)a.N, 128);
+  CUtensorMap tR0 = a.residual ? make_tmap_2d(a.residual, prec, (uint64_t)a.M, (uint64_t)a.N, 128) : tD0;
+  CUtensorMap tA1 = make_tmap_2d(b.a, prec, (uint64_t)b.M, (uint64_t)b.K, 128);
+  CUtensorMap tB1 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, BN);
+  CUtensorMap tD1 = make_tmap_2d(b.y, prec, (uint64_t)b.M, (uint64_t)b.N, 128);
+  CUtensorMap tR1 = b.residual ? make_tmap_2d(b.residual, prec, (uint64_t)b.M, (uint64_t)b.N, 128) : tD1;
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA0, tB0, tD0, tR0, tA1, tB1, tD1, tR1, p);
+  HFR_LAUNCH_CHECK("gemm_chain");
+}
+void launch_zero_u32(unsigned* p, size_t n, cudaStream_t s) {
+  if (n == 0) return;
+  launch_pdl(zero_u32_kernel, dim3(grid_for((long long)(n / 4), 256)), dim3(256), 0, s, reinterpret_cast<uint4*>(p), n / 4);
+  HFR_LAUNCH_CHECK("zero_u32");
+}
+void launch_gemm_chain(const GemmArgs& a, const GemmArgs& b, int prec, int device, unsigned* done, cudaStream_t s) {
+  if (!gemm_chain_eligible(a, b, prec, device)) throw Error(-5, "gemm chain: the two layers do not form an eligible pair");
+  if (prec == PREC_BF16) launch_gemm_chain_t<__nv_bfloat16>(a, b, prec, device, done, s);
+  else launch_gemm_chain_t<float>(a, b, prec, device, done, s);
+}
+
 // ---------------------------------------------------------------------------------------------- implicit-GEMM conv
 void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s) {
   if (prec == PREC_FP32) throw Error(-5, "KxK convolutions run on the tensor-core path only (tf32 / bf16 precision)");
@@ -448,14 +520,15 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- window conv
+// shared-memory plan of the window kernel for `stages` ring slots and `passes` weight sweeps
 static void window_smem(int cin, int kh, int kw, int* w_bytes, int* win_bytes, int* win_stride, int* total,
-                        bool shifted = false) {
+                        bool shifted = false, int stages = kWinStagesMin, int passes = 1) {
   const int planes = cin / 8;
-  *w_bytes = kh * kw * planes * 64 * 16;
+  *w_bytes = kh * kw * planes * 64 * 16 * passes;
   *win_bytes = shifted ? kw * planes * (16 + kh - 1) * 128
                        : planes * (((16 + kh - 1) * (8 + kw - 1) * 16 + 127) / 128 * 128);  // planes at a 128-B pitch
   *win_stride = (*win_bytes + 1023) / 1024 * 1024;
-  *total = 1024 + *w_bytes + kWinStages * *win_stride + 4 * 16384 + 256;
+  *total = 1024 + *w_bytes + stages * *win_stride + 4 * 16384 + 256;
 }
 bool conv_window_fits(int cin, int kh, int kw) {
   if (cin % 16) return false;
@@ -480,13 +553,19 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   int w_bytes, win_bytes, win_stride, total;
   static const bool no_shifted = getenv("HFR_NO_SHIFTED") != nullptr;
   const bool shifted = a.plane_major && !no_shifted;
-  window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total, shifted);
   if (a.passes != 1 && a.passes != 2) throw Error(-1, "window conv: passes must be 1 or 2");
-  if (a.passes == 2) {  // second sweep of taps (bf16 residual of the weights) resident next to the first
-    total += w_bytes;
-    w_bytes *= 2;
-  }
+  // (passes == 2: a second sweep of taps - the bf16 residual of the weights - is resident next to the first)
+  static const int stage_cap = getenv("HFR_WIN_STAGES") ? atoi(getenv("HFR_WIN_STAGES")) : kWinStagesMax;
+  int stages = kWinStagesMin;
+  window_smem(a.cin, a.kh, a.kw, &w_bytes, &win_bytes, &win_stride, &total, shifted, stages, a.passes);
   if (total > 227 * 1024) throw Error(-5, "window conv: shared memory budget exceeded");
+  while (stages < kWinStagesMax && stages < stage_cap) {   // as deep a ring as fits: the depth hides the window load latency
+    int wb, wn, ws, tot;
+    window_smem(a.cin, a.kh, a.kw, &wb, &wn, &ws, &tot, shifted, stages + 1, a.passes);
+    if (tot > 227 * 1024) break;
+    ++stages;
+    total = tot;
+  }
   const int planes = a.cin / 8;
   const int ww = 8 + a.kw - 1, wh = 16 + a.kh - 1;
   CUtensorMap tX;
@@ -525,6 +604,7 @@ void launch_conv_window(const WinArgs& a, int device, cudaStream_t s) {
   p.shifted = shifted;
   p.copy_pitch = planes * wh * 128;
   p.round_tf32 = a.round_tf32;
+  p.stages = stages;
   const int grid = p.num_tiles < device_sm_count(device) ? p.num_tiles : device_sm_count(device);
   if (grid < 1) return;
   if (a.out_f32 || a.passes == 2) {  // experimental tf32-mode stem: fp32 output, two weight sweeps
@@ -657,12 +737,9 @@ void launch_resize_pil(const uint8_t* images, const long long* desc, int* tab, i
   const size_t smem = (size_t)taps_v * ow * 3;
   if (smem > 200 * 1024) throw Error(-5, "PIL resize: output row cache exceeds shared memory");
   if (n > 65535) throw Error(-1, "PIL resize: at most 65535 images per call");
-  static std::atomic<bool> configured{false};
-  if (smem > 48 * 1024 && !configured.load()) {
+  if (smem > 48 * 1024)   // per device and cheap: set on every call rather than cached in a process-wide flag
     cuda_check(cudaFuncSetAttribute(resize_pil_bilinear_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                "cudaFuncSetAttribute(pil resize smem)");
-    configured.store(true);
-  }
   pil_coeff_kernel<<<dim3((unsigned)((ow + oh + 127) / 128), (unsigned)n), 128, 0, s>>>(desc, tab, oh, ow, taps_h, taps_v);
   HFR_LAUNCH_CHECK("pil_coeff");
   resize_pil_bilinear_u8_kernel<<<dim3((unsigned)oh, (unsigned)n), 256, smem, s>>>(images, desc, tab, out, oh, ow, taps_h,

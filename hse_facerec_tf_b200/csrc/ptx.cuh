@@ -60,6 +60,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// Two independent fp32 FMAs in one instruction (sm_100 FFMA2): a0 += x0 * w0, a1 += x1 * w1, each rounded exactly like
+// fmaf - bit-identical results at half the issue slots.  The operands are register pairs; ptxas places the values in
+// adjacent registers, so the packing moves disappear.
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float x0, float x1, float w0, float w1) {
+  asm("{\n\t.reg .b64 xx, ww, cc;\n\t"
+      "mov.b64 xx, {%2, %3};\n\t"
+      "mov.b64 ww, {%4, %5};\n\t"
+      "mov.b64 cc, {%0, %1};\n\t"
+      "fma.rn.f32x2 cc, xx, ww, cc;\n\t"
+      "mov.b64 {%0, %1}, cc;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(x0), "f"(x1), "f"(w0), "f"(w1));
+}
+
 // 16-byte read-only global load that does not allocate in L1 (streamed once: residual rows in the GEMM epilogue)
 __device__ __forceinline__ uint4 ld_global_nc_v4(const uint4* p) {
   uint4 v;

@@ -106,8 +106,8 @@ class TensorFlowInference:
     def extract_stream(self, batches, l2norm=False, depth=2):
         """The dataset loop of facerec_test.py:394 with batches instead of single files: an iterable of host batches
         ([B,H,W,3] uint8 RGB crops, or float32 already pre-processed) -> a generator of [B,D] float32 arrays, `depth`
-        batches in flight so that uploads and downloads overlap the compute.  Each yielded array is reused `depth`
-        batches later - copy it (np.vstack / .copy()) if it has to outlive that."""
+        batches in flight so that uploads and downloads overlap the compute.  A yielded array is valid only until the
+        next item is requested (its pinned buffer is resubmitted then) - copy it (np.vstack / .copy()) to keep it."""
         for (out,) in self.model.stream_host(batches, depth=depth, convert2BGR=self.convert2BGR,
                                              imageNetUtilsMean=self.imageNetUtilsMean, l2norm=l2norm, graph=True):
             yield out

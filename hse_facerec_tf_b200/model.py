@@ -84,6 +84,8 @@ class HfrModel:
         pre-processed (what the reference feeds the placeholder).  Returns a list of float32 CUDA tensors."""
         if not (x.is_cuda and x.is_contiguous()):
             raise ValueError("x must be a contiguous CUDA tensor")
+        if x.device != self.device:
+            raise ValueError(f"x lives on {x.device}, the model on {self.device}")
         if x.dim() != 4 or tuple(x.shape[1:]) != (self.h, self.w, self.c):
             raise ValueError(f"expected input [B,{self.h},{self.w},{self.c}], got {tuple(x.shape)}")
         if x.dtype == torch.uint8:
@@ -95,9 +97,12 @@ class HfrModel:
         B = x.shape[0]
         if outs is None:
             outs = [torch.empty((B, d), dtype=torch.float32, device=x.device) for d in self.out_dims]
+        elif any(o.device != self.device or o.dtype != torch.float32 or not o.is_contiguous() for o in outs):
+            raise ValueError("outs must be contiguous float32 tensors on the model's device")
         ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
         flags = self._flags(convert2BGR, imageNetUtilsMean, l2norm, graph, dt == _lib.IN_U8)
-        check(lib.hfr_model_forward(self._h, x.data_ptr(), dt, B, flags, ptrs, _stream_ptr(x.device)))
+        with torch.cuda.device(self.device):     # the library selects the model's device; torch's current one is restored
+            check(lib.hfr_model_forward(self._h, x.data_ptr(), dt, B, flags, ptrs, _stream_ptr(x.device)))
         return outs
 
     def forward_host(self, x: np.ndarray, convert2BGR=True, imageNetUtilsMean=True, l2norm=False, graph=False,
@@ -148,8 +153,9 @@ class HfrModel:
 
     def stream_host(self, batches, depth=2, **kw):
         """Generator over an iterable of host batches -> lists of page-locked float32 outputs, `depth` batches in flight
-        (upload of batch i+1 and download of batch i-1 overlap the compute of batch i).  Each yielded list is reused
-        `depth` batches later: copy what must outlive that."""
+        (upload of batch i+1 and download of batch i-1 overlap the compute of batch i).  A yielded list is valid ONLY
+        until the next item is requested: its slot (and its pinned output arrays) is resubmitted at that moment - copy
+        what must outlive that."""
         depth = max(1, min(int(depth), self.HOST_SLOTS))
         pinned, pending, bufs = {}, [], {}
         for i, x in enumerate(batches):

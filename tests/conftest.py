@@ -12,16 +12,23 @@ AGE_GENDER_PB = os.path.join(GOLDEN, "age_gender_quantized.pb")
 
 
 def _ensure_library():
-    """A fresh checkout has no libhfr.so (built artefacts are git-ignored): build it (nvcc cross-compiles without a
-    GPU) before any test imports the package.  build.py is loaded by path - importing the package would dlopen the
+    """Built artefacts are git-ignored: (re)build libhfr.so before any test imports the package - build.py skips every
+    object that is newer than its sources, so an up-to-date library costs nothing and a stale one cannot be tested by
+    accident.  On the GPU box the snapshot ships the library already built (and nvcc may be absent): a build failure is
+    only fatal when there is no library at all.  build.py is loaded by path - importing the package would dlopen the
     library it is about to build."""
-    if os.path.exists(os.path.join(ROOT, "hse_facerec_tf_b200", "libhfr.so")):
-        return           # present (built here, or shipped to the GPU box with the snapshot): never rebuild behind a test run
     import importlib.util
+    have_lib = os.path.exists(os.path.join(ROOT, "hse_facerec_tf_b200", "libhfr.so"))
+    if have_lib and os.environ.get("GRAFT_REPO_ROOT"):
+        return           # gpurun snapshot on the GPU box: the library travelled prebuilt, file times did not necessarily
     spec = importlib.util.spec_from_file_location("_hfr_build", os.path.join(ROOT, "hse_facerec_tf_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.build()
+    try:
+        mod.build()
+    except Exception:
+        if not os.path.exists(os.path.join(ROOT, "hse_facerec_tf_b200", "libhfr.so")):
+            raise
 
 
 def pytest_configure(config):

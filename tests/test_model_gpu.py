@@ -364,3 +364,41 @@ def test_tf32_tensor_core_stem_matches_the_cuda_core_stem(age_gender_pb, monkeyp
         err = float((stem_got - stem_want).abs().max()) / (float(stem_want.abs().max()) + 1.0)
         assert err < 2e-3, f"stem output differs: {err}"          # both are rounded to tf32 (2^-11) on store
         assert cosine(got.cpu().numpy(), want.cpu().numpy()).min() > 0.99999
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_chained_gemm_pairs_are_bit_identical_to_separate_launches(precision, tmp_path, monkeypatch):
+    """gemm_chain_kernel (an 'increase' 1x1 convolution and the next block's 'reduce' in one persistent launch, the
+    second reading the first's rows through L2 behind release/acquire counters) computes every tile exactly like the
+    two separate launches: same K order, same epilogue.  ResNet-50 at batch 128 chains the pairs of stages 2 and 3;
+    the outputs must be identical bit for bit, eagerly, under graph replay and when repeated (counter reset)."""
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    pb = write_resnet50_pb(str(tmp_path / "vgg2_resnet.pb"), seed=7)
+    u8 = np.concatenate([smooth_images(16, 224, 4), np.random.RandomState(3).randint(0, 256, (112, 224, 224, 3)).astype(np.uint8)])
+    x = torch.from_numpy(u8).cuda()
+    monkeypatch.setenv("HFR_CHAIN", "0")
+    m0 = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    (want,) = m0.forward(x, True, False)
+    n0 = hfr.launch_count()
+    m0.forward(x, True, False)
+    separate = hfr.launch_count() - n0
+    monkeypatch.delenv("HFR_CHAIN")
+    m1 = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    n0 = hfr.launch_count()
+    (got,) = m1.forward(x, True, False)
+    chained = hfr.launch_count() - n0
+    assert chained < separate, (chained, separate)              # pairs really went through the chained kernel
+    torch.testing.assert_close(got, want, rtol=0, atol=0)
+    for _ in range(3):
+        (again,) = m1.forward(x, True, False, graph=True)
+        torch.testing.assert_close(again, want, rtol=0, atol=0)
+    # layer by layer (every intermediate of both halves of a pair is still written)
+    m0.keep_activations(True)
+    m1.keep_activations(True)
+    monkeypatch.setenv("HFR_CHAIN", "0")
+    m0.forward(x[:32].contiguous(), True, False)
+    monkeypatch.delenv("HFR_CHAIN")
+    m1.forward(x[:32].contiguous(), True, False)
+    for li in range(len(m0.plan()["layers"])):
+        a, b = m0.layer_output(li, 32), m1.layer_output(li, 32)
+        assert torch.equal(a, b), f"layer {li} {m0.plan()['layers'][li]['name']}"

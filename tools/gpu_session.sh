@@ -4,6 +4,7 @@
 # Every stage writes into gpurun_out/ (merged back by gpurun) and appends one line to gpurun_out/summary.txt.
 # Stages:
 #   tests            pytest -m gpu (whole suite)
+#   pytest:<expr>[:timeout]  pytest -m gpu -k <expr>
 #   experimental     the opt-in tests of the experimental switches (HFR_TEST_EXPERIMENTAL=1)
 #   bench            bench.py default line (all workloads) -> bench_all.json
 #   bench:<w>[:tf32] one workload, per-layer timings -> bench_<w>[_tf32].json
@@ -29,6 +30,9 @@ for stage in "$@"; do
     tests)
       timeout -k 5 900 $PY -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
       note "tests rc=$? $(tail -1 gpurun_out/pytest_gpu.log)";;
+    pytest)   # pytest:<-k expression>: a subset of the GPU tests under a short timeout (new kernels first)
+      timeout -k 5 ${b:-300} $PY -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider -k "$a" > gpurun_out/pytest_$i.log 2>&1
+      note "pytest -k '$a' rc=$? $(tail -1 gpurun_out/pytest_$i.log)";;
     experimental)
       HFR_TEST_EXPERIMENTAL=1 timeout -k 5 600 $PY -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k experimental \
         > gpurun_out/pytest_experimental.log 2>&1

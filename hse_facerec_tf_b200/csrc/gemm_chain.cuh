@@ -9,11 +9,14 @@
 // (lag x 128 rows, a few MB) - the HBM read of Y disappears, and so does one launch.
 //
 // Correct ordering between CTAs: a producer tile is published - done[m] += 1, release at gpu scope - once its TMA stores
-// have completed; the epilogue warpgroup does that one of ITS tiles later (by then the stores are long complete, the
-// wait costs nothing).  The TMA producer warp of a consumer tile acquires done[m] == column blocks of Y before it
-// requests the rows.  Dependencies only point to units at least lag * (units per row block) earlier; the launcher keeps
-// that distance above four waves of the grid, so a CTA's own unpublished tile (at most two of its tiles back) is never
-// what its producer warp waits for, and the unit with the smallest index is always runnable: no deadlock.
+// have completed.  In steady state the epilogue warpgroup does that while it finishes its NEXT tile (the stores are long
+// complete by then, the wait costs nothing; waiting right after a tile's own stores serialised the epilogue on the store
+// latency and made the pair 1.6x slower than two launches).  A warpgroup never blocks with an unpublished tile, though:
+// if its next accumulator is not ready it publishes first.  The TMA producer warp of a consumer tile acquires
+// done[m] == column blocks of Y before it requests the rows.  Dependencies only point to earlier units, every CTA walks
+// its units in order and nobody blocks while holding an unpublished tile, so the unit with the smallest index is always
+// runnable: no deadlock for any grid size or lag.  (The first deferred version published only from inside the next tile
+// and deadlocked in the sparse tail of the schedule, where that next tile can depend on the unpublished one.)
 //
 // Same warp roles, rings, TMEM double buffering and epilogue as gemm_tc_kernel (1-CTA tiles, 2-D operands).
 #pragma once
@@ -31,8 +34,8 @@ struct ChainProblem {
 struct ChainParams {
   ChainProblem pr[2];    // 0: producer GEMM (writes Y), 1: consumer GEMM (its A operand is Y)
   int M, num_m_blocks;
-  int lag;               // the consumer trails the producer by this many row blocks
-  int num_units;         // (num_m_blocks + lag) * (pr[0].num_n_blocks + pr[1].num_n_blocks)
+  int lag;               // row blocks per super-block: the consumer works one super-block behind the producer
+  int num_units;         // (ceil(num_m_blocks / lag) + 1) * lag * (pr[0].num_n_blocks + pr[1].num_n_blocks)
   unsigned* done;        // [num_m_blocks] finished producer tiles per row block, zero when the launch starts
 };
 
@@ -45,6 +48,14 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void tma_store_wait_all_but() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -79,6 +90,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint8_t* sEpi_gen = smem_gen + STAGES * SM::kStageBytes;
   const uint32_t sBar = sEpi + SM::kEpiBytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sEpi_gen + SM::kEpiBytes + 192);
+  const uint32_t dep_ready = sBar + 200u;   // consumer tiles of this CTA whose rows are known to be published
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 64u + 8u * s; };
   auto tfull_bar = [&](int s) { return sBar + 128u + 8u * s; };
@@ -102,6 +114,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(tempty_bar(s), 4);
     }
     for (int s = 0; s < 4; ++s) mbar_init(rfull_bar(s), 1);
+    st_release_cta_shared(dep_ready, 0u);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS, 1>(smem_u32(tmem_slot));
@@ -116,12 +129,20 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int G = nb0 + nb1;
   // unit -> (problem, row block, column block); false: the unit is a hole of the schedule (before the consumer starts
   // or after the producer has finished)
+  // Phased order: super-blocks of p.lag row blocks; super-block s = [producer tiles of its rows][consumer tiles of the
+  // rows of super-block s - 1].  Within a phase all tiles have the same K, so the load ring keeps its look-ahead (with
+  // the two kinds interleaved tile by tile a K = 256 consumer tile took 4 of the 5 slots and the HBM-latency-bound
+  // producer tiles around it lost their prefetch depth).
+  const int R = p.lag, SP = R * nb0, S = R * G;
   auto decode = [&](int u, int& q, int& mb, int& nb) -> bool {
-    const int g = u / G, r = u - g * G;
-    if (r < nb0) {
-      q = 0; mb = g; nb = r;
+    const int sb = u / S, r = u - sb * S;
+    if (r < SP) {
+      const int i = r / nb0;
+      q = 0; mb = sb * R + i; nb = r - i * nb0;
     } else {
-      q = 1; mb = g - p.lag; nb = r - nb0;
+      const int r2 = r - SP, i = r2 / nb1;
+      q = 1; mb = (sb - 1) * R + i; nb = r2 - i * nb1;
+      if (sb == 0) return false;
     }
     return mb >= 0 && mb < p.num_m_blocks;
   };
@@ -129,16 +150,17 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, consumer_idx = 0;   // consumer tiles of this CTA handed to the loader so far
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       int q, mb, nb;
       if (!decode(u, q, mb, nb)) continue;
-      if (q == 1) {   // rows of Y: every producer tile of this row block has completed its stores
+      if (q == 1) {   // rows of Y: warp 3 has seen every producer tile of this row block published
         if (lane == 0) {
-          while (ld_acquire_gpu(p.done + mb) < (unsigned)nb0) __nanosleep(32);
-          fence_proxy_async_all();   // the acquired writes were made by the async proxy (TMA stores); so are our reads
+          while (ld_acquire_cta_shared(dep_ready) <= consumer_idx) __nanosleep(20);
+          fence_proxy_async_all();   // the published rows were written by the async proxy (TMA stores); so are our reads
         }
         __syncwarp();
+        ++consumer_idx;
       }
       const CUtensorMap* ta = q ? &tmA1 : &tmA0;
       const CUtensorMap* tb = q ? &tmB1 : &tmB0;
@@ -155,6 +177,21 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           stage = 0;
           phase ^= 1;
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ dependency scout
+    // Walks this CTA's consumer tiles in order, well ahead of the loader, and polls their row block's counter with
+    // gpu-scope acquire loads (an L2 round trip each - on the loader's own path they cost ~1 us per consumer tile);
+    // the loader then only reads a shared-memory count.
+    if (lane == 0) {
+      uint32_t seen = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int q, mb, nb;
+        if (!decode(u, q, mb, nb) || q == 0) continue;
+        while (ld_acquire_gpu(p.done + mb) < (unsigned)nb0) __nanosleep(64);
+        ++seen;
+        st_release_cta_shared(dep_ready, seen);
       }
     }
   } else if (warp == 1) {
@@ -255,6 +292,16 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool use_res = (P.residual != nullptr);
       const uint32_t aphase = my_tiles & 1;
       ++my_tiles;
+      if (leader && pub_mb >= 0 && !mbar_try_wait(tfull_bar(as), aphase)) {
+        // This tile's accumulator is not ready, i.e. we are about to block - possibly on a consumer tile that (through
+        // other CTAs) waits for the very tile we have not published yet (sparse tail of the schedule: the next valid
+        // tile of this warpgroup can be many waves away).  Never block holding an unpublished tile: publish now; the
+        // wait for the stores overlaps the wait for the MMAs.
+        tma_store_wait_all();
+        fence_proxy_async_all();
+        red_release_gpu_add(p.done + pub_mb, 1u);
+        pub_mb = -1;
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
@@ -364,7 +411,6 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // wait is free; waiting right after a tile's own stores serialised the epilogue on the store latency.
             tma_store_wait_all_but<1>();
             fence_proxy_async_all();
-            __threadfence();
             red_release_gpu_add(p.done + pub_mb, 1u);
             pub_mb = -1;
           }
@@ -379,7 +425,6 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       tma_store_wait_all();
       if (pub_mb >= 0) {
         fence_proxy_async_all();
-        __threadfence();
         red_release_gpu_add(p.done + pub_mb, 1u);
       }
     }

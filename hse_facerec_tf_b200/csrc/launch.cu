@@ -348,9 +348,9 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------- chained GEMM pair
-static int chain_mode() {   // HFR_CHAIN=0: never; unset / 1: pairs whose layers both run as 1-CTA tiles; 2: every eligible pair
+static int chain_mode() {   // unset / HFR_CHAIN=0: never (measured slower); 1: pairs whose layers both run as 1-CTA tiles; 2: every eligible pair
   const char* e = getenv("HFR_CHAIN");   // read per call (host-side, once per launch): tests flip it between models
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }
 bool gemm_chain_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int device) {
   if (chain_mode() == 0 || prec == PREC_FP32) return false;
@@ -392,9 +392,11 @@ static void launch_gemm_chain_t(const GemmArgs& a, const GemmArgs& b, int prec, 
   p.num_m_blocks = (int)((a.M + 127) / 128);
   const int G = p.pr[0].num_n_blocks + p.pr[1].num_n_blocks;
   const int grid = device_sm_count(device);
-  p.lag = (6 * grid + G - 1) / G + 1;                // the consumer trails by ~6 waves of units (>= 4 is required, see the
-                                                     // kernel header): its rows are published by then and still in L2
-  p.num_units = (p.num_m_blocks + p.lag) * G;
+  // super-block = `waves` waves of producer tiles: long enough that its rows are published before the consumer phase
+  // reaches them, short enough that they are still in L2 (2 waves of stage-2 tiles: 9.5 MB of Y behind 21 MB of traffic)
+  static const int waves = getenv("HFR_CHAIN_LAG") ? std::max(1, atoi(getenv("HFR_CHAIN_LAG"))) : 2;
+  p.lag = std::max(1, waves * grid / p.pr[0].num_n_blocks);
+  p.num_units = ((p.num_m_blocks + p.lag - 1) / p.lag + 1) * p.lag * G;
   p.done = done;
   CUtensorMap tA0 = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
   CUtensorMap tB0 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, BN);

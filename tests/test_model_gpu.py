@@ -382,7 +382,7 @@ def test_chained_gemm_pairs_are_bit_identical_to_separate_launches(precision, tm
     n0 = hfr.launch_count()
     m0.forward(x, True, False)
     separate = hfr.launch_count() - n0
-    monkeypatch.delenv("HFR_CHAIN")
+    monkeypatch.setenv("HFR_CHAIN", "1")
     m1 = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
     n0 = hfr.launch_count()
     (got,) = m1.forward(x, True, False)
@@ -397,7 +397,7 @@ def test_chained_gemm_pairs_are_bit_identical_to_separate_launches(precision, tm
     m1.keep_activations(True)
     monkeypatch.setenv("HFR_CHAIN", "0")
     m0.forward(x[:32].contiguous(), True, False)
-    monkeypatch.delenv("HFR_CHAIN")
+    monkeypatch.setenv("HFR_CHAIN", "1")
     m1.forward(x[:32].contiguous(), True, False)
     for li in range(len(m0.plan()["layers"])):
         a, b = m0.layer_output(li, 32), m1.layer_output(li, 32)

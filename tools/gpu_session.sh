@@ -30,9 +30,12 @@ for stage in "$@"; do
     tests)
       timeout -k 5 900 $PY -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
       note "tests rc=$? $(tail -1 gpurun_out/pytest_gpu.log)";;
-    pytest)   # pytest:<-k expression>: a subset of the GPU tests under a short timeout (new kernels first)
+    pytest)   # pytest:<-k expression>[:timeout]: a subset of the GPU tests under a short timeout (new kernels first);
+              # a failure or a hang ENDS the session - nothing else is run on top of a kernel that does not work
       timeout -k 5 ${b:-300} $PY -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider -k "$a" > gpurun_out/pytest_$i.log 2>&1
-      note "pytest -k '$a' rc=$? $(tail -1 gpurun_out/pytest_$i.log)";;
+      rc=$?
+      note "pytest -k '$a' rc=$rc $(tail -1 gpurun_out/pytest_$i.log)"
+      if [ $rc -ne 0 ]; then cat $S; exit $rc; fi;;
     experimental)
       HFR_TEST_EXPERIMENTAL=1 timeout -k 5 600 $PY -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k experimental \
         > gpurun_out/pytest_experimental.log 2>&1
@@ -43,14 +46,14 @@ for stage in "$@"; do
         note "bench (all workloads) rc=$?"
       else
         P=bf16; T=""; [ "$b" = tf32 ] && { P=tf32; T=_tf32; }
-        timeout -k 5 600 $PY bench.py --only $a --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
+        timeout -k 5 ${STAGE_TIMEOUT:-600} $PY bench.py --only $a --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
           > gpurun_out/bench_$a$T.json 2> gpurun_out/bench_$a$T.err
         note "bench $a $P rc=$?"
       fi;;
     ab)
       P=bf16; T=""; [ "$c" = tf32 ] && { P=tf32; T=_tf32; }
       tag=$(echo "$a" | tr -d '=')
-      env "$a" timeout -k 5 600 $PY bench.py --only $b --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
+      env "$a" timeout -k 5 ${STAGE_TIMEOUT:-600} $PY bench.py --only $b --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
         > gpurun_out/bench_$b${T}_$tag.json 2> gpurun_out/bench_$b${T}_$tag.err
       note "ab $a $b $P rc=$?";;
     peaks)

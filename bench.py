@@ -180,11 +180,11 @@ def plan_work(plan, es):
             in_b, out_b = L["cin"] * 4, L["cout"] * 4
         if L["in2"] >= 0:
             in_b += ho * wo * L["cout"] * es
-        rows.append(dict(kind=kind, name=L["name"], flops=flops, bytes=float(in_b + out_b)))
+        rows.append(dict(kind=kind, name=L["name"], flops=flops, bytes=float(in_b + out_b), out_bytes=float(out_b)))
     return rows
 
 
-KERNEL_NAMES = {"pw": "gemm_tc_kernel (1x1 conv)", "fc": "dense_heads_kernel",
+KERNEL_NAMES = {"pw": "gemm_tc_kernel / gemm_pair_kernel (1x1 conv)", "fc": "dense_heads_kernel",
                 "conv": "gemm_tc_kernel (im2col) / conv_window_kernel", "dw": "dwconv3x3_pipe_kernel"}
 
 
@@ -308,8 +308,16 @@ def bench_network(workload, precision, args, rank, world, dev):
     while i < len(work):
         w, t = dict(work[i]), per_step[i]
         if t < 0:
-            i += 1      # nothing launched (the library reports -1): bypassed gather, or a layer fused into a neighbour's kernel
+            i += 1      # nothing launched (the library reports -1): a bypassed gather
             continue
+        if w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 0:
+            # gemm_pair_kernel: this 1x1 convolution and the next one in ONE launch.  The launch's algorithmic work is both
+            # layers' flops and this layer's bytes plus the second layer's OUTPUT only (its input never leaves the SM)
+            w2 = work[i + 1]
+            w["name"] += " + " + w2["name"]
+            w["flops"] += w2["flops"]
+            w["bytes"] += w2["out_bytes"]
+            i += 1
         merged.append((w, t))
         i += 1
     for w, t in merged:

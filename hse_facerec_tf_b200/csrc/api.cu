@@ -426,18 +426,8 @@ struct hfr_model {
     graphs.clear();
   }
 
-  // counters of the chained GEMM pairs (gemm_chain.cuh) live behind the activations: one per 128 rows of the largest map
-  static constexpr size_t kChainCounterBytes = 4 << 20;
-  unsigned* chain_counters(int batch) const { return (unsigned*)((char*)arena.p + per_image_bytes * (size_t)batch); }
-  // does the plan hold an 1x1 -> 1x1 pair at all?  (then a pass starts by clearing the pairs' counters)
-  bool plan_has_pw_pairs() const {
-    for (size_t i = 0; i + 1 < plan.layers.size(); ++i)
-      if (plan.layers[i].kind == L_PW && plan.layers[i + 1].kind == L_PW && plan.layers[i + 1].in == plan.layers[i].out) return true;
-    return false;
-  }
-
   void ensure_arena(int batch) {
-    const size_t need = per_image_bytes * (size_t)batch + kChainCounterBytes;
+    const size_t need = per_image_bytes * (size_t)batch;
     if (need > arena.bytes) {
       drop_graphs();
       arena.ensure(need);
@@ -465,9 +455,6 @@ struct hfr_model {
     const size_t in_img_bytes = (size_t)plan.in_h * plan.in_w * plan.in_c * (in_dtype == HFR_IN_U8 ? 1 : 4);
     const void* x = (const char*)x_all + (size_t)img0 * in_img_bytes;
     std::vector<char> launched(plan.layers.size(), 1);
-    size_t chain_cursor = 0;   // counters handed to the chained pairs of this pass so far
-    if (prec != HFR_FP32 && total == batch && plan_has_pw_pairs())
-      launch_zero_u32(chain_counters(total), kChainCounterBytes / 4, s);
     auto vptr = [&](int v) -> void* { return (char*)val_ptr(v, total) + (size_t)img0 * value_exact_bytes(v); };
     for (size_t i = 0; i < plan.layers.size(); ++i) {
       const Layer& L = plan.layers[i];
@@ -580,20 +567,17 @@ struct hfr_model {
           a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
           a.y = out; a.M = (int64_t)batch * L.Ho * L.Wo; a.N = L.cout; a.K = L.cin;
           a.act = act; a.round_tf32 = round_out;
-          // the next layer is a plain 1x1 convolution over this layer's output: both GEMMs in one persistent launch,
-          // the second reading the first's rows while they are still in L2 (gemm_chain.cuh)
-          if (i + 1 < plan.layers.size() && total == batch) {
+          // the next layer is a plain 1x1 convolution over this layer's output (the seam between two bottleneck blocks):
+          // both GEMMs in one launch, the second fed from the first's staged output chunks (gemm_pair.cuh)
+          if (i + 1 < plan.layers.size()) {
             const Layer& N2 = plan.layers[i + 1];
-            const size_t m_blocks = (size_t)((a.M + 127) / 128 + 3) / 4 * 4;
-            if (N2.kind == L_PW && N2.in == L.out && gather_of[i + 1] < 0 && chain_cursor + m_blocks <= kChainCounterBytes / 4) {
+            if (N2.kind == L_PW && N2.in == L.out && N2.in2 < 0 && gather_of[i + 1] < 0) {
               GemmArgs b;
-              b.a = out; b.b = dev[i + 1].w; b.bias = dev[i + 1].bias;
-              b.residual = N2.in2 >= 0 ? vptr(N2.in2) : nullptr;
+              b.a = out; b.b = dev[i + 1].w; b.bias = dev[i + 1].bias; b.residual = nullptr;
               b.y = vptr(N2.out); b.M = a.M; b.N = N2.cout; b.K = N2.cin;
               b.act = N2.act; b.round_tf32 = rt && feeds_tensor_core(N2.out);
-              if (b.residual != out && gemm_chain_eligible(a, b, prec, device)) {
-                launch_gemm_chain(a, b, prec, device, chain_counters(total) + chain_cursor, s);
-                chain_cursor += m_blocks;
+              if (gemm_pair_eligible(a, b, prec, device)) {
+                launch_gemm_pair(a, b, prec, device, s);
                 if (timing) {
                   cuda_check(cudaEventRecord(ev[2 * i + 1], s), "cudaEventRecord");
                   cuda_check(cudaEventRecord(ev[2 * i + 2], s), "cudaEventRecord");

@@ -10,7 +10,7 @@
 #include <mutex>
 
 #include "conv_window.cuh"
-#include "gemm_chain.cuh"
+#include "gemm_pair.cuh"
 #include "kernels.cuh"
 
 namespace hfr {
@@ -347,77 +347,67 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
   else launch_gemm_store<float, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
 }
 
-// ---------------------------------------------------------------------------------------------- chained GEMM pair
-static int chain_mode() {   // unset / HFR_CHAIN=0: never (measured slower); 1: pairs whose layers both run as 1-CTA tiles; 2: every eligible pair
-  const char* e = getenv("HFR_CHAIN");   // read per call (host-side, once per launch): tests flip it between models
-  return e ? atoi(e) : 0;
+// ---------------------------------------------------------------------------------------------- fused GEMM pair
+// HFR_SEAM=0: never fuse an 'increase' 1x1 convolution with the next block's 'reduce'; unset / 1: fuse every eligible pair.
+// HFR_SEAM_BUFS=2|3 staging buffers per epilogue warpgroup, HFR_SEAM_PF=1|2 residual prefetch distance (A/B knobs).
+static int seam_mode() {
+  const char* e = getenv("HFR_SEAM");   // read per call (host side, once per launch): tests flip it between models
+  return e ? atoi(e) : 1;
 }
-bool gemm_chain_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int device) {
-  if (chain_mode() == 0 || prec == PREC_FP32) return false;
+bool gemm_pair_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int device) {
+  (void)device;
+  if (seam_mode() == 0 || prec == PREC_FP32) return false;
   const int es = (int)elt_size(prec);
   if (a.M != b.M || b.a != a.y || a.N != b.K || a.M <= 0 || a.M >= (1ll << 31)) return false;
-  if ((a.K * es) % 16 || (b.K * es) % 16 || (a.N * es) % 128 || (b.N * es) % 128) return false;
-  if (a.N % 128) return false;                       // the producer's tiles are whole 128-column blocks
-  const int sms = device_sm_count(device);
-  if ((a.M + 127) / 128 < 4 * sms) return false;     // short launches: nothing to overlap, the lag would cover the whole problem
-  if (chain_mode() == 1) {
-    int ctas, bn;
-    gemm_tile_choice(a.M, a.N, a.K, 0, sms, &ctas, &bn);
-    if (ctas != 1) return false;
-    gemm_tile_choice(b.M, b.N, b.K, 0, sms, &ctas, &bn);
-    if (ctas != 1) return false;
-  }
+  if (b.residual != nullptr) return false;
+  if ((a.K * es) % 16 || a.N % 128) return false;     // whole 128-column tiles of Y; TMA row pitch
+  if (b.N != 64 && b.N != 128 && b.N != 256) return false;   // the second accumulator: one tile of N2 TMEM columns
   return true;
 }
-
-template <typename T>
-static void launch_gemm_chain_t(const GemmArgs& a, const GemmArgs& b, int prec, int device, unsigned* done, cudaStream_t s) {
-  constexpr int BN = 128;
-  using SM = GemmSmem<BN, EPI_STORE, 1>;
-  auto kern = gemm_chain_kernel<T, BN>;
+template <typename T, int N2, int NBUF, int PF>
+static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+  using SM = PairSmem<NBUF>;
+  auto kern = gemm_pair_kernel<T, N2, NBUF, PF>;
   static std::atomic<bool> configured[64];
   if (!configured[device].load()) {
     cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal),
-               "cudaFuncSetAttribute(gemm chain smem)");
+               "cudaFuncSetAttribute(gemm pair smem)");
     configured[device].store(true);
   }
-  ChainParams p;
+  PairParams p;
   memset(&p, 0, sizeof(p));
-  const GemmArgs* g[2] = {&a, &b};
-  for (int q = 0; q < 2; ++q) {
-    p.pr[q].N = g[q]->N; p.pr[q].K = g[q]->K; p.pr[q].num_n_blocks = (g[q]->N + BN - 1) / BN;
-    p.pr[q].bias = g[q]->bias; p.pr[q].residual = g[q]->residual; p.pr[q].act = g[q]->act; p.pr[q].round_tf32 = g[q]->round_tf32;
-  }
-  p.M = (int)a.M;
-  p.num_m_blocks = (int)((a.M + 127) / 128);
-  const int G = p.pr[0].num_n_blocks + p.pr[1].num_n_blocks;
-  const int grid = device_sm_count(device);
-  // super-block = `waves` waves of producer tiles: long enough that its rows are published before the consumer phase
-  // reaches them, short enough that they are still in L2 (2 waves of stage-2 tiles: 9.5 MB of Y behind 21 MB of traffic)
-  static const int waves = getenv("HFR_CHAIN_LAG") ? std::max(1, atoi(getenv("HFR_CHAIN_LAG"))) : 2;
-  p.lag = std::max(1, waves * grid / p.pr[0].num_n_blocks);
-  p.num_units = ((p.num_m_blocks + p.lag - 1) / p.lag + 1) * p.lag * G;
-  p.done = done;
-  CUtensorMap tA0 = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
-  CUtensorMap tB0 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, BN);
-  CUtensorMap tD0 = make_tmap_2d(a.y, prec, (uint64_t)a.M, (uint64_t)a.N, 128);
-  CUtensorMap tR0 = a.residual ? make_tmap_2d(a.residual, prec, (uint64_t)a.M, (uint64_t)a.N, 128) : tD0;
-  CUtensorMap tA1 = make_tmap_2d(b.a, prec, (uint64_t)b.M, (uint64_t)b.K, 128);
-  CUtensorMap tB1 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, BN);
-  CUtensorMap tD1 = make_tmap_2d(b.y, prec, (uint64_t)b.M, (uint64_t)b.N, 128);
-  CUtensorMap tR1 = b.residual ? make_tmap_2d(b.residual, prec, (uint64_t)b.M, (uint64_t)b.N, 128) : tD1;
-  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA0, tB0, tD0, tR0, tA1, tB1, tD1, tR1, p);
-  HFR_LAUNCH_CHECK("gemm_chain");
+  p.M = (int)a.M; p.num_m_blocks = (int)((a.M + 127) / 128);
+  p.N1 = a.N; p.K1 = a.K;
+  p.bias1 = a.bias; p.residual = a.residual; p.act1 = a.act; p.round1 = a.round_tf32;
+  p.bias2 = b.bias; p.act2 = b.act; p.round2 = b.round_tf32;
+  const int grid = std::min(device_sm_count(device), p.num_m_blocks);
+  CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
+  CUtensorMap tB1 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, 128);
+  CUtensorMap tD1 = make_tmap_2d(a.y, prec, (uint64_t)a.M, (uint64_t)a.N, 128);
+  CUtensorMap tR = a.residual ? make_tmap_2d(a.residual, prec, (uint64_t)a.M, (uint64_t)a.N, 128) : tD1;
+  CUtensorMap tB2 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, (uint32_t)N2);
+  CUtensorMap tD2 = make_tmap_2d(b.y, prec, (uint64_t)b.M, (uint64_t)b.N, 128);
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB1, tD1, tR, tB2, tD2, p);
+  HFR_LAUNCH_CHECK("gemm_pair");
 }
-void launch_zero_u32(unsigned* p, size_t n, cudaStream_t s) {
-  if (n == 0) return;
-  launch_pdl(zero_u32_kernel, dim3(grid_for((long long)(n / 4), 256)), dim3(256), 0, s, reinterpret_cast<uint4*>(p), n / 4);
-  HFR_LAUNCH_CHECK("zero_u32");
+template <typename T, int N2>
+static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+  static const int bufs = getenv("HFR_SEAM_BUFS") ? atoi(getenv("HFR_SEAM_BUFS")) : 3;
+  static const int pf = getenv("HFR_SEAM_PF") ? atoi(getenv("HFR_SEAM_PF")) : 1;
+  if (bufs == 3 && pf == 2) launch_gemm_pair_inst<T, N2, 3, 2>(a, b, prec, device, s);
+  else if (bufs == 3) launch_gemm_pair_inst<T, N2, 3, 1>(a, b, prec, device, s);
+  else launch_gemm_pair_inst<T, N2, 2, 1>(a, b, prec, device, s);
 }
-void launch_gemm_chain(const GemmArgs& a, const GemmArgs& b, int prec, int device, unsigned* done, cudaStream_t s) {
-  if (!gemm_chain_eligible(a, b, prec, device)) throw Error(-5, "gemm chain: the two layers do not form an eligible pair");
-  if (prec == PREC_BF16) launch_gemm_chain_t<__nv_bfloat16>(a, b, prec, device, done, s);
-  else launch_gemm_chain_t<float>(a, b, prec, device, done, s);
+template <typename T>
+static void launch_gemm_pair_t(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+  if (b.N == 64) launch_gemm_pair_n2<T, 64>(a, b, prec, device, s);
+  else if (b.N == 128) launch_gemm_pair_n2<T, 128>(a, b, prec, device, s);
+  else launch_gemm_pair_n2<T, 256>(a, b, prec, device, s);
+}
+void launch_gemm_pair(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+  if (!gemm_pair_eligible(a, b, prec, device)) throw Error(-5, "gemm pair: the two layers do not form an eligible pair");
+  if (prec == PREC_BF16) launch_gemm_pair_t<__nv_bfloat16>(a, b, prec, device, s);
+  else launch_gemm_pair_t<float>(a, b, prec, device, s);
 }
 
 // ---------------------------------------------------------------------------------------------- implicit-GEMM conv

@@ -87,12 +87,10 @@ struct GemmArgs {
   int act, round_tf32;
 };
 void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s);
-// Two dependent GEMMs in one persistent launch (gemm_chain.cuh): second.a must be first.y, same M.  `done` is device
-// scratch of at least ceil(M / 128) counters that are ZERO when the kernel starts (launch_zero_u32; n a multiple of 4).  gemm_chain_eligible: both would run as 1-CTA
-// tiles and the shapes fit the chained kernel.
-bool gemm_chain_eligible(const GemmArgs& first, const GemmArgs& second, int prec, int device);
-void launch_zero_u32(unsigned* p, size_t n, cudaStream_t s);
-void launch_gemm_chain(const GemmArgs& first, const GemmArgs& second, int prec, int device, unsigned* done, cudaStream_t s);
+// Two dependent 1x1 convolutions in one launch (gemm_pair.cuh): second.a must be first.y, same M, second.N in
+// {64, 128, 256}, no residual on the second; the second GEMM's A operand never leaves shared memory.
+bool gemm_pair_eligible(const GemmArgs& first, const GemmArgs& second, int prec, int device);
+void launch_gemm_pair(const GemmArgs& first, const GemmArgs& second, int prec, int device, cudaStream_t s);
 // fp32-accurate y[M, N] = act(a[M,K] b[N,K]^T + bias) on the tensor cores (3xTF32, kernels.cuh); ldy >= N is y's row
 // pitch in floats.  Needs K % 4 == 0; scratch comes from the stream-ordered allocator.
 void launch_gemm_x3(const float* a, const float* b, const float* bias, float* y, int64_t M, int N, int K, int64_t ldy, int act,

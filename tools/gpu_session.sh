@@ -8,7 +8,7 @@
 #   experimental     the opt-in tests of the experimental switches (HFR_TEST_EXPERIMENTAL=1)
 #   bench            bench.py default line (all workloads) -> bench_all.json
 #   bench:<w>[:tf32] one workload, per-layer timings -> bench_<w>[_tf32].json
-#   ab:<ENV>=<v>:<w>[:tf32]  one workload with an environment switch set -> bench_<w>[_tf32]_<ENV><v>.json
+#   ab:<ENV>=<v>[,<ENV2>=<v2>]:<w>[:tf32]  one workload with environment switches set -> bench_<w>[_tf32]_<ENV><v>.json
 #   peaks            tools/peak_probe.py -> peaks_probe.json (bf16 / tf32 matmul, HBM copy)
 #   launches:<w>     ncu launch list (gpu__time_duration) of one eager step -> launches_<w>.csv
 #   ncu:<w>:<kernel regex>:<skip>:<count>[:tf32]   ncu --set full of matching launches -> prof_<w>_<n>.ncu-rep
@@ -52,8 +52,8 @@ for stage in "$@"; do
       fi;;
     ab)
       P=bf16; T=""; [ "$c" = tf32 ] && { P=tf32; T=_tf32; }
-      tag=$(echo "$a" | tr -d '=')
-      env "$a" timeout -k 5 ${STAGE_TIMEOUT:-600} $PY bench.py --only $b --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
+      tag=$(echo "$a" | tr -d '=,')
+      env ${a//,/ } timeout -k 5 ${STAGE_TIMEOUT:-600} $PY bench.py --only $b --precision $P --steps 30 --warmup 3 --layers --no-cpu-baseline \
         > gpurun_out/bench_$b${T}_$tag.json 2> gpurun_out/bench_$b${T}_$tag.err
       note "ab $a $b $P rc=$?";;
     peaks)

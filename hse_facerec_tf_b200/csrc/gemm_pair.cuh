@@ -12,8 +12,12 @@
 // are drained like any other tile.  The K order of the second GEMM (chunks in ascending column order, four K-slices
 // each) is the order the stand-alone kernel uses, so Z is bit-identical to two separate launches.
 //
-//   warp 0        TMA producer, one ring of 32 KB slots:  per Y tile  K1/BK slots {A k-block, W1 k-block}, then the
-//                 W2 K-blocks of the PREVIOUS Y tile (N2 rows x 128 bytes each, as many as fit a slot)
+//   warp 0        TMA producer of the weight ring (16 KB slots):  per Y tile  K1/BK slots of W1 k-blocks, then the W2
+//                 K-blocks of the PREVIOUS Y tile (N2 rows x 128 bytes each: two per slot for N2 = 64, two slots = two
+//                 128-column halves for N2 = 256)
+//   warp 3        TMA producer of the unit's A rows: all K1/BK k-blocks of a 128-row block stay RESIDENT for the unit's
+//                 N1/128 Y tiles (re-streaming them per tile made stages 3-4 L2->SM-bound: 8 x 64 KB per unit in stage
+//                 4); double-buffered across units when K1 <= 2 k-blocks
 //   warp 1        MMA issuer:  GEMM1(tile q) into accumulator stage q & 1, then GEMM2 of tile q-1 (its chunks are being
 //                 staged by an epilogue warpgroup while GEMM1(q) runs), commit -> sfree[buffer], last chunk -> zfull
 //   warp 2        TMEM allocator (512 columns: 2 x 128 for Y tiles, N2 <= 256 for Z)
@@ -40,15 +44,22 @@ struct PairParams {
   int act1, round1;
   const float* bias2;    // [N2] or nullptr
   int act2, round2;
+  int na;                // A buffers (units in flight): 2 when K1 <= 2 k-blocks, else 1
+  int stages;            // 16 KB slots of the weight ring (what is left of the shared memory, <= 8)
 };
 
-template <int NBUF>
 struct PairSmem {
-  static constexpr int kSlotBytes = 32768;                 // {A k-block, W1 k-block} or W2 k-blocks
-  static constexpr int kEpiBytes = 2 * NBUF * 16384;       // 2 warpgroups x NBUF staging buffers
+  static constexpr int kSlotBytes = 16384;                 // one k-block: 128 rows x 128 bytes
   static constexpr int kBarBytes = 512;
-  static constexpr int kStages = (227 * 1024 - 1024 - kBarBytes - kEpiBytes) / kSlotBytes;   // NBUF 2: 5, 3: 4
-  static constexpr int kTotal = 1024 + kStages * kSlotBytes + kEpiBytes + kBarBytes;
+  static constexpr int kMax = 227 * 1024;
+  // dynamic shared memory: [1 KB alignment slack][na x num_kb A k-blocks][stages ring slots][2 x nbuf staging][barriers]
+  static int stages_for(int num_kb, int na, int nbuf) {
+    const int n = (kMax - 1024 - kBarBytes - (na * num_kb + 2 * nbuf) * kSlotBytes) / kSlotBytes;
+    return n > 8 ? 8 : n;
+  }
+  static int total(int num_kb, int na, int nbuf, int stages) {
+    return 1024 + (na * num_kb + stages + 2 * nbuf) * kSlotBytes + kBarBytes;
+  }
 };
 
 template <typename T, int N2, int NBUF, int PF>
@@ -57,34 +68,41 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmD1, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2, const PairParams p) {
   using TR = GemmTraits<T>;
-  using SM = PairSmem<NBUF>;
-  constexpr int STAGES = SM::kStages;
+  constexpr int SLOT = PairSmem::kSlotBytes;
   constexpr int BK = TR::BK;
   constexpr int CH_ELEMS = 128 / (int)sizeof(T);     // columns per 128-byte chunk = one K-block of the second GEMM
   constexpr int NCHUNK = 128 / CH_ELEMS;             // chunks per Y tile (2 bf16, 4 tf32)
   constexpr int ZCH = N2 / CH_ELEMS;                 // chunks of a Z tile
-  constexpr int B2_BYTES = N2 * 128;                 // one K-block of W2
-  constexpr int CPS = (SM::kSlotBytes / B2_BYTES) < NCHUNK ? (SM::kSlotBytes / B2_BYTES) : NCHUNK;  // W2 K-blocks per slot
+  constexpr int HALVES = (N2 == 256) ? 2 : 1;        // a W2 K-block of 256 rows travels as two 128-row slots
+  constexpr int N2H = N2 / HALVES;                   // columns per second-GEMM MMA
+  constexpr int B2_BYTES = N2H * 128;                // bytes of one W2 K-block (half) in its slot
+  constexpr int CPS = (N2 == 64) ? 2 : 1;            // W2 K-blocks per slot
   constexpr uint32_t ACC2_COL = 256;
   static_assert(N2 == 64 || N2 == 128 || N2 == 256, "N2");
-  static_assert(NBUF >= 2 && NBUF <= 3 && PF >= 1 && PF < NBUF, "staging buffers / prefetch distance");
+  static_assert(NBUF >= 2 && NBUF <= 4 && PF >= 1 && PF < NBUF, "staging buffers / prefetch distance");
   static_assert(NCHUNK % CPS == 0, "W2 K-blocks per slot");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t sRing = smem_base;
-  const uint32_t sEpi = smem_base + STAGES * SM::kSlotBytes;
-  const uint32_t sBar = sEpi + SM::kEpiBytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * SM::kSlotBytes + SM::kEpiBytes + 320);
+  const int num_kb = (p.K1 + BK - 1) / BK;
+  const int STAGES = p.stages, NA = p.na;
+  const uint32_t a_bytes = (uint32_t)num_kb * SLOT;
+  const uint32_t sA = smem_base;
+  const uint32_t sRing = sA + (uint32_t)NA * a_bytes;
+  const uint32_t sEpi = sRing + (uint32_t)STAGES * SLOT;
+  const uint32_t sBar = sEpi + 2u * NBUF * SLOT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (sBar - smem_base) + 400);
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 64u + 8u * s; };
   auto tfull_bar = [&](int s) { return sBar + 128u + 8u * s; };
   auto tempty_bar = [&](int s) { return sBar + 144u + 8u * s; };
-  auto rfull_bar = [&](int s) { return sBar + 160u + 8u * s; };   // residual chunk landed in staging buffer s
-  auto sfull_bar = [&](int s) { return sBar + 208u + 8u * s; };   // Y chunk staged in buffer s (GEMM2 may read it)
-  auto sfree_bar = [&](int s) { return sBar + 256u + 8u * s; };   // the GEMM2 MMAs that read buffer s have retired
-  const uint32_t zfull_bar = sBar + 304u, zempty_bar = sBar + 312u;
+  auto afull_bar = [&](int s) { return sBar + 160u + 8u * s; };   // the unit's A rows are resident in A buffer s
+  auto aempty_bar = [&](int s) { return sBar + 176u + 8u * s; };  // the unit's last GEMM1 has retired
+  auto rfull_bar = [&](int s) { return sBar + 192u + 8u * s; };   // residual chunk landed in staging buffer s
+  auto sfull_bar = [&](int s) { return sBar + 256u + 8u * s; };   // Y chunk staged in buffer s (GEMM2 may read it)
+  auto sfree_bar = [&](int s) { return sBar + 320u + 8u * s; };   // the GEMM2 MMAs that read buffer s have retired
+  const uint32_t zfull_bar = sBar + 384u, zempty_bar = sBar + 392u;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -104,6 +122,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
     }
     for (int s = 0; s < 2 * NBUF; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -123,7 +143,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_wait();
 
   const int T1 = p.N1 / 128;                        // Y tiles per unit
-  const int num_kb = (p.K1 + BK - 1) / BK;
   const int my_units = ((int)blockIdx.x < p.num_m_blocks) ? (p.num_m_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -139,28 +158,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto load_w2 = [&](int j) {   // the W2 K-blocks that meet Y tile j's chunks
 #pragma unroll
       for (int c = 0; c < NCHUNK; c += CPS) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), CPS * B2_BYTES);
 #pragma unroll
-          for (int cc = 0; cc < CPS; ++cc)
-            tma_load_2d(sRing + stage * SM::kSlotBytes + cc * B2_BYTES, &tmB2, full_bar(stage),
-                        j * 128 + (c + cc) * CH_ELEMS, 0);
+        for (int h = 0; h < HALVES; ++h) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), CPS * B2_BYTES);
+#pragma unroll
+            for (int cc = 0; cc < CPS; ++cc)
+              tma_load_2d(sRing + stage * SLOT + cc * B2_BYTES, &tmB2, full_bar(stage), j * 128 + (c + cc) * CH_ELEMS, h * 128);
+          }
+          __syncwarp();
+          advance();
         }
-        __syncwarp();
-        advance();
       }
     };
     int prev_j = -1;
     for (int ul = 0; ul < my_units; ++ul) {
-      const int mb = (int)blockIdx.x + ul * (int)gridDim.x;
       for (int j = 0; j < T1; ++j) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(full_bar(stage), SM::kSlotBytes);
-            tma_load_2d(sRing + stage * SM::kSlotBytes, &tmA, full_bar(stage), kb * BK, mb * 128);
-            tma_load_2d(sRing + stage * SM::kSlotBytes + 16384, &tmB1, full_bar(stage), kb * BK, j * 128);
+            mbar_expect_tx(full_bar(stage), SLOT);
+            tma_load_2d(sRing + stage * SLOT, &tmB1, full_bar(stage), kb * BK, j * 128);
           }
           __syncwarp();
           advance();
@@ -170,11 +189,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (prev_j >= 0) load_w2(prev_j);
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer of the units' A rows
+    for (int ul = 0; ul < my_units; ++ul) {
+      const int mb = (int)blockIdx.x + ul * (int)gridDim.x;
+      const int ab = ul % NA;
+      mbar_wait(aempty_bar(ab), (uint32_t)((ul / NA) & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(afull_bar(ab), a_bytes);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(sA + (uint32_t)ab * a_bytes + kb * SLOT, &tmA, afull_bar(ab), kb * BK, mb * 128);
+      }
+      __syncwarp();
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     constexpr uint32_t idesc1 = umma_idesc(TR::kFmt, 128, 128);
-    constexpr uint32_t idesc2 = umma_idesc(TR::kFmt, 128, N2);
-    const uint64_t ring_desc0 = umma_desc_sw128(sRing), epi_desc0 = umma_desc_sw128(sEpi);
+    constexpr uint32_t idesc2 = umma_idesc(TR::kFmt, 128, N2H);
+    const uint64_t ring_desc0 = umma_desc_sw128(sRing), epi_desc0 = umma_desc_sw128(sEpi), a_desc0 = umma_desc_sw128(sA);
     int stage = 0;
     uint32_t phase = 0;
     auto advance = [&]() {
@@ -193,24 +225,27 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        if (c % CPS == 0) mbar_wait(full_bar(stage), phase);
         const uint32_t bi = wg * NBUF + (base + c) % NBUF;
         mbar_wait(sfull_bar(bi), (sfull_par >> bi) & 1u);
         sfull_par ^= 1u << bi;
-        tc_fence_after();
-        const uint32_t a_off = (bi * 16384u) >> 4;
-        const uint32_t b_off = (uint32_t)(stage * SM::kSlotBytes + (c % CPS) * B2_BYTES) >> 4;
-        if (elect_one()) {
+        const uint32_t a_off = (bi * (uint32_t)SLOT) >> 4;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma<TR::kTF32>(tmem_base + ACC2_COL, epi_desc0 + a_off + 2u * k, ring_desc0 + b_off + 2u * k, idesc2,
-                            (j | c | k) != 0);
-          umma_commit(sfree_bar(bi));
-          if (c % CPS == CPS - 1) umma_commit(empty_bar(stage));
-          if (j == T1 - 1 && c == NCHUNK - 1) umma_commit(zfull_bar);
+        for (int h = 0; h < HALVES; ++h) {
+          if (c % CPS == 0) mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t b_off = (uint32_t)(stage * SLOT + (c % CPS) * B2_BYTES) >> 4;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma<TR::kTF32>(tmem_base + ACC2_COL + h * 128, epi_desc0 + a_off + 2u * k, ring_desc0 + b_off + 2u * k, idesc2,
+                              (j | c | k) != 0);
+            if (h == HALVES - 1) umma_commit(sfree_bar(bi));
+            if (c % CPS == CPS - 1) umma_commit(empty_bar(stage));
+            if (j == T1 - 1 && c == NCHUNK - 1 && h == HALVES - 1) umma_commit(zfull_bar);
+          }
+          __syncwarp();
+          if (c % CPS == CPS - 1) advance();
         }
-        __syncwarp();
-        if (c % CPS == CPS - 1) advance();
       }
     };
     int prev_ul = -1, prev_j = 0;
@@ -222,16 +257,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 128;
+        const int ab = ul % NA;
+        if (j == 0) {   // the unit's A rows are resident
+          mbar_wait(afull_bar(ab), (uint32_t)((ul / NA) & 1));
+          tc_fence_after();
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_off = (uint32_t)(stage * SM::kSlotBytes) >> 4, b_off = a_off + (16384u >> 4);
+          const uint32_t a_off = ((uint32_t)ab * a_bytes + (uint32_t)kb * SLOT) >> 4, b_off = (uint32_t)(stage * SLOT) >> 4;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma<TR::kTF32>(d_tmem, ring_desc0 + a_off + 2u * k, ring_desc0 + b_off + 2u * k, idesc1, (kb | k) != 0);
+              umma<TR::kTF32>(d_tmem, a_desc0 + a_off + 2u * k, ring_desc0 + b_off + 2u * k, idesc1, (kb | k) != 0);
             umma_commit(empty_bar(stage));
-            if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+            if (kb == num_kb - 1) {
+              umma_commit(tfull_bar(as));
+              if (j == T1 - 1) umma_commit(aempty_bar(ab));   // the A buffer may take the next unit's rows
+            }
           }
           __syncwarp();
           advance();
@@ -275,8 +318,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const int ul = pf_i / JT, j = pf_i - ul * JT;
       if (j < T1 && use_res) {
-        mbar_expect_tx(rfull_bar(bi), 16384);
-        tma_load_2d(sEpi + bi * 16384, &tmR, rfull_bar(bi), j * 128 + pf_c * CH_ELEMS,
+        mbar_expect_tx(rfull_bar(bi), SLOT);
+        tma_load_2d(sEpi + bi * SLOT, &tmR, rfull_bar(bi), j * 128 + pf_c * CH_ELEMS,
                     ((int)blockIdx.x + ul * (int)gridDim.x) * 128);
       }
       ++pf_ctr;
@@ -312,7 +355,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < nch; ++c, ++ctr) {
         const int n0 = (isZ ? 0 : j * 128) + c * CH_ELEMS;
         const uint32_t b = ctr % NBUF, bi = g * NBUF + b;
-        const uint32_t st_row = sEpi + bi * 16384 + row * 128;
+        const uint32_t st_row = sEpi + bi * SLOT + row * 128;
         if (leader) prefetch();   // the chunk PF ahead: frees its buffer (used NBUF - PF chunks ago), requests its residual
         uint4 rv[8];
         if (res) {
@@ -402,7 +445,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (leader) {
-          tma_store_2d(isZ ? &tmD2 : &tmD1, sEpi + bi * 16384, n0, mb * 128);
+          tma_store_2d(isZ ? &tmD2 : &tmD1, sEpi + bi * SLOT, n0, mb * 128);
           tma_store_commit();
           if (!isZ) mbar_arrive(sfull_bar(bi));   // the chunk is complete in shared memory: GEMM2 may read it
         }

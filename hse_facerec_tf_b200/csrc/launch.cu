@@ -349,10 +349,14 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------- fused GEMM pair
 // HFR_SEAM=0: never fuse an 'increase' 1x1 convolution with the next block's 'reduce'; unset / 1: fuse every eligible pair.
-// HFR_SEAM_BUFS=2|3 staging buffers per epilogue warpgroup, HFR_SEAM_PF=1|2 residual prefetch distance (A/B knobs).
+// HFR_SEAM_BUFS=2|3|4 staging buffers per epilogue warpgroup (4: residual prefetched two chunks ahead) - A/B knob.
 static int seam_mode() {
   const char* e = getenv("HFR_SEAM");   // read per call (host side, once per launch): tests flip it between models
   return e ? atoi(e) : 1;
+}
+static int pair_num_kb(int K, int prec) {   // 128-byte k-blocks of the first GEMM
+  const int bk = 128 / (int)elt_size(prec);
+  return (K + bk - 1) / bk;
 }
 bool gemm_pair_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int device) {
   (void)device;
@@ -362,15 +366,15 @@ bool gemm_pair_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int devi
   if (b.residual != nullptr) return false;
   if ((a.K * es) % 16 || a.N % 128) return false;     // whole 128-column tiles of Y; TMA row pitch
   if (b.N != 64 && b.N != 128 && b.N != 256) return false;   // the second accumulator: one tile of N2 TMEM columns
+  if (pair_num_kb(a.K, prec) > 4) return false;       // the unit's A rows stay resident in shared memory (<= 64 KB)
   return true;
 }
 template <typename T, int N2, int NBUF, int PF>
 static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
-  using SM = PairSmem<NBUF>;
   auto kern = gemm_pair_kernel<T, N2, NBUF, PF>;
   static std::atomic<bool> configured[64];
   if (!configured[device].load()) {
-    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal),
+    cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kMax),
                "cudaFuncSetAttribute(gemm pair smem)");
     configured[device].store(true);
   }
@@ -380,21 +384,27 @@ static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec
   p.N1 = a.N; p.K1 = a.K;
   p.bias1 = a.bias; p.residual = a.residual; p.act1 = a.act; p.round1 = a.round_tf32;
   p.bias2 = b.bias; p.act2 = b.act; p.round2 = b.round_tf32;
+  const int num_kb = pair_num_kb(a.K, prec);
+  p.na = num_kb <= 2 ? 2 : 1;
+  p.stages = PairSmem::stages_for(num_kb, p.na, NBUF);
   const int grid = std::min(device_sm_count(device), p.num_m_blocks);
   CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
   CUtensorMap tB1 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, 128);
   CUtensorMap tD1 = make_tmap_2d(a.y, prec, (uint64_t)a.M, (uint64_t)a.N, 128);
   CUtensorMap tR = a.residual ? make_tmap_2d(a.residual, prec, (uint64_t)a.M, (uint64_t)a.N, 128) : tD1;
-  CUtensorMap tB2 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, (uint32_t)N2);
+  CUtensorMap tB2 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, (uint32_t)std::min(N2, 128));
   CUtensorMap tD2 = make_tmap_2d(b.y, prec, (uint64_t)b.M, (uint64_t)b.N, 128);
-  launch_pdl(kern, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB1, tD1, tR, tB2, tD2, p);
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)PairSmem::total(num_kb, p.na, NBUF, p.stages), s, tA, tB1, tD1, tR, tB2, tD2, p);
   HFR_LAUNCH_CHECK("gemm_pair");
 }
 template <typename T, int N2>
 static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
-  static const int bufs = getenv("HFR_SEAM_BUFS") ? atoi(getenv("HFR_SEAM_BUFS")) : 3;
-  static const int pf = getenv("HFR_SEAM_PF") ? atoi(getenv("HFR_SEAM_PF")) : 1;
-  if (bufs == 3 && pf == 2) launch_gemm_pair_inst<T, N2, 3, 2>(a, b, prec, device, s);
+  static const int bufs_env = getenv("HFR_SEAM_BUFS") ? atoi(getenv("HFR_SEAM_BUFS")) : 0;
+  const int num_kb = pair_num_kb(a.K, prec);
+  int bufs = bufs_env ? bufs_env : 4;   // 4: residual chunks requested two ahead (stage 2: 192 -> 172 us per seam)
+  // the weight ring keeps at least 4 slots: fewer staging buffers when the resident A rows are large
+  while (bufs > 2 && PairSmem::stages_for(num_kb, num_kb <= 2 ? 2 : 1, bufs) < 4) --bufs;
+  if (bufs >= 4) launch_gemm_pair_inst<T, N2, 4, 2>(a, b, prec, device, s);
   else if (bufs == 3) launch_gemm_pair_inst<T, N2, 3, 1>(a, b, prec, device, s);
   else launch_gemm_pair_inst<T, N2, 2, 1>(a, b, prec, device, s);
 }

@@ -389,7 +389,8 @@ def test_fused_gemm_pairs_are_bit_identical_to_separate_launches(precision, batc
     n0 = hfr.launch_count()
     (got,) = m1.forward(x, True, False)
     fused = hfr.launch_count() - n0
-    assert fused <= separate - 8, (fused, separate)             # the seams really went through the fused kernel
+    # the seams really went through the fused kernel: 8 in bf16; tf32's stage 4 (K = 8 k-blocks of A) is not eligible
+    assert fused <= separate - (8 if precision == "bf16" else 4), (fused, separate)
     torch.testing.assert_close(got, want, rtol=0, atol=0)
     for _ in range(3):
         (again,) = m1.forward(x, True, False, graph=True)

@@ -1,7 +1,7 @@
-"""Per-source-line stall samples from an ncu report.  usage: python tools/ncu_lines.py <rep> [top]"""
+"""Per-source-line stall samples from an ncu report.  usage: python tools/ncu_lines.py <rep> [top [launch-skip]]"""
 import collections, csv, subprocess, sys
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--launch-count", "1"],
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30; skip = sys.argv[3] if len(sys.argv) > 3 else "0"
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--launch-skip", skip, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 cur_file = cur = None

@@ -251,7 +251,7 @@ def bench_network(workload, precision, args, rank, world, dev):
             # Streaming form (hfr_model_submit_host / hfr_model_wait_host, `depth` batches in flight): every step's
             # input still travels pinned host -> device and its result device -> pinned host inside the timed region,
             # but step i+1's upload and step i-1's download overlap step i's compute.
-            depth = int(os.environ.get("HFR_BENCH_E2E_DEPTH", "2"))
+            depth = int(os.environ.get("HFR_BENCH_E2E_DEPTH", "3"))
             hx = [torch.from_numpy(synth_images(batch, size, 5000 + 1000 * rank + i)).pin_memory() for i in range(depth)]
             houts = [[torch.empty((batch, d), dtype=torch.float32).pin_memory().numpy() for d in model.out_dims]
                      for _ in range(depth)]
@@ -368,7 +368,7 @@ def bench_network(workload, precision, args, rank, world, dev):
     if e2e_s is not None:
         rec["e2e"] = dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
                           d2h_bytes_per_step=sum(out_dims) * 4 * batch,
-                          note=f"hfr_model_submit_host/wait_host, {os.environ.get('HFR_BENCH_E2E_DEPTH', '2')} batches in "
+                          note=f"hfr_model_submit_host/wait_host, {os.environ.get('HFR_BENCH_E2E_DEPTH', '3')} batches in "
                                f"flight; host in submit {host_s[0] / steps * 1e3:.3f} ms, in wait {host_s[1] / steps * 1e3:.3f} "
                                "ms per step. e2e can exceed `value`: the device-resident loop draws more power and sits "
                                "lower under the board's power cap")

@@ -12,6 +12,8 @@ UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e
 
 def kernel_class(name):
     """class from the kernel name alone (fallback when the plan is not available)"""
+    if "gemm_pair_kernel" in name:
+        return "pw"
     if "gemm_tc_kernel" in name:
         mode = name.split("<")[1].split(">")[0].replace(" ", "").split(",")
         epi, amode = mode[2], mode[3]
@@ -38,11 +40,20 @@ def plan_classes(workload):
     m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
     layers = m.plan()["layers"]
     seq = []
+    sub_outs = {L["out"] for L in layers if L["kind"] == "subsample"}
+    fused_into_prev = False
     for i, L in enumerate(layers):
         if L["kind"] == "subsample":
             users = [U for U in layers if U["in"] == L["out"] or U.get("in2", -1) == L["out"]]
             if users and all(U["kind"] == "pw" and U["in"] == L["out"] for U in users):
                 continue
+        if fused_into_prev:          # second half of a gemm_pair_kernel launch (launch.cu: gemm_pair_eligible, bf16)
+            fused_into_prev = False
+            continue
+        if L["kind"] == "pw" and i + 1 < len(layers) and L["in"] not in sub_outs:
+            N = layers[i + 1]
+            fused_into_prev = (N["kind"] == "pw" and N["in"] == L["out"] and N.get("in2", -1) < 0 and L["cout"] % 128 == 0
+                               and N["cout"] in (64, 128, 256) and (L["cin"] + 63) // 64 <= 4)
         seq += ["stem", "stem"] if L["kind"] == "stem" else [L["kind"]]
     return seq
 

@@ -572,7 +572,7 @@ def run_reference(args):
     steps as the product arm.  The headline runs the full K steps + W warm-ups of the full batch; the other workloads
     run a few steps each so that the whole arm ends within a few minutes."""
     if args.only:
-        print(json.dumps(reference_record(args.only, args, args.steps, args.warmup)))
+        emit(reference_record(args.only, args, args.steps, args.warmup))
         return
     rec = reference_record(HEADLINE[0], args, args.steps, args.warmup)
     rec["workloads"] = {}
@@ -580,7 +580,16 @@ def run_reference(args):
         if prec != "bf16" and w == HEADLINE[0]:
             continue        # the CPU arm has one precision (fp32): resnet50_tf32 compares with the headline record
         rec["workloads"][w] = reference_record(w, args, min(args.steps, 5), 1)
-    print(json.dumps(rec))
+    emit(rec)
+
+
+_OUT = None
+
+
+def emit(rec):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(rec) + "\n")
+    out.flush()
 
 
 def main():
@@ -599,6 +608,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--layers", action="store_true", help="add per-layer event timings to the JSON line")
     args = ap.parse_args()
+    # ONE JSON line on stdout: everything else that writes to file descriptor 1 (NCCL prints its version banner there,
+    # from C) goes to stderr; the record is written through a private duplicate of the original stdout
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -642,7 +657,7 @@ def main():
         if rank == 0:
             res["workloads"] = others
     if rank == 0:
-        print(json.dumps(res))
+        emit(res)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

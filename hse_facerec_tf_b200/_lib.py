@@ -42,6 +42,10 @@ SIGNATURES = {
     "hfr_knn_query": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "hfr_knn_query_host": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "hfr_knn_merge": (_i, [_vp, _i, _i64, _i, _vp, _i, _vp]),
+    "hfr_knn_query_partial": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "hfr_knn_merge_certify": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "hfr_knn_query_exact": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "hfr_knn_merge_listed": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "hfr_knn_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "hfr_knn_debug_candidates": (_i64, [_vp, _vp, _vp, _i64]),
     "hfr_knn_free": (None, [_vp]),

@@ -128,11 +128,30 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
         stream = _stream_ptr(q.device)
         # hfr_neighbor records {double dist2; int64 index} as one int64 tensor [nq, k, 2]
         out = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
-        check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, int(k), out.data_ptr(), stream))
-        if self.sharded:
+        if not self.sharded:
+            check(lib.hfr_knn_query(self._knn, q.data_ptr(), nq, int(k), out.data_ptr(), stream))
+            self._sharded_unc = None
+        else:
+            # Row-sharded gallery (include/hfr.h, "Row-sharded gallery, exact and shard-independent"): every shard
+            # proposes its re-scored candidates plus a lower bound for everything it did not re-score; after ONE
+            # all-gather the global answer is certified against the smallest bound.  Only queries that fail it (the
+            # same list on every rank) go through the shards' fp64 passes and a second exchange.
             from .parallel import gather_neighbors
-            parts = gather_neighbors(out, self.process_group)          # ONE all-gather of the packed records
-            check(lib.hfr_knn_merge(parts.data_ptr(), parts.shape[0], nq, int(k), out.data_ptr(), dev, stream))
+            part = torch.empty((nq, k + 1, 2), dtype=torch.int64, device=q.device)
+            check(lib.hfr_knn_query_partial(self._knn, q.data_ptr(), nq, int(k), part.data_ptr(), stream))
+            parts = gather_neighbors(part, self.process_group)
+            unc = torch.empty((nq + 1,), dtype=torch.int32, device=q.device)     # [0]: count, [1:]: the list
+            check(lib.hfr_knn_merge_certify(parts.data_ptr(), parts.shape[0], nq, int(k), out.data_ptr(),
+                                            unc[1:].data_ptr(), unc.data_ptr(), dev, stream))
+            n_unc = int(unc[:1].cpu()[0])
+            if n_unc:
+                loc = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
+                check(lib.hfr_knn_query_exact(self._knn, q.data_ptr(), nq, int(k), unc[1:].data_ptr(), unc.data_ptr(),
+                                              loc.data_ptr(), stream))
+                parts2 = gather_neighbors(loc, self.process_group)
+                check(lib.hfr_knn_merge_listed(parts2.data_ptr(), parts2.shape[0], nq, int(k), unc[1:].data_ptr(),
+                                               unc.data_ptr(), out.data_ptr(), dev, stream))
+            self._sharded_unc = (nq, n_unc)
         self._last_out = out
         rec = out.cpu().numpy()
         ind = np.ascontiguousarray(rec[:, :, 1])
@@ -144,6 +163,9 @@ class KNeighborsClassifier(ClassifierMixin, BaseEstimator):
     def query_stats(self):
         """(queries certified by the rounding bound, queries re-scored exactly against the whole shard) of the last
         kneighbors call on this rank."""
+        if getattr(self, "_sharded_unc", None) is not None:     # sharded: certified globally, after the exchange
+            nq, n_unc = self._sharded_unc
+            return nq - n_unc, n_unc
         a, b = C.c_int64(), C.c_int64()
         check(lib.hfr_knn_stats(self._knn, C.byref(a), C.byref(b)))
         return a.value, b.value

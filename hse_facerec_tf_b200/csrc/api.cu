@@ -1078,7 +1078,8 @@ int hfr_knn_set_gallery(hfr_knn* k, const float* gallery, int64_t n_local, int64
   });
 }
 
-int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream) {
+static int knn_query_impl(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream,
+                          int partial) {
   return guarded([&] {
     if (!k || !queries || !out || nq < 0) throw Error(HFR_ERR_INVALID, "bad argument");
     if (n_neighbors < 1 || n_neighbors > 4) throw Error(HFR_ERR_UNSUPPORTED, "k-NN on the GPU path supports 1 <= n_neighbors <= 4");
@@ -1118,10 +1119,54 @@ int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors,
     f.cand = cand; f.nq = nq; f.n = k->n_local; f.d = k->dim; f.row_offset = k->row_offset; f.k = n_neighbors;
     f.precision = k->precision; f.gmax2 = (const float*)k->g_max2.p; f.out = out;
     f.unc_list = (int*)k->unc_list.p; f.counters = (int*)k->counters.p; f.locks = (int*)k->locks.p;
+    f.partial = partial;
     launch_knn_finalize(f, k->device, s);
     k->last_nq = nq;
     k->last_records = splits * 2 * cand;
     k->last_stream = s;
+  });
+}
+
+int hfr_knn_query(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream) {
+  return knn_query_impl(k, queries, nq, n_neighbors, out, stream, 0);
+}
+
+int hfr_knn_query_partial(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream) {
+  return knn_query_impl(k, queries, nq, n_neighbors, out, stream, 1);
+}
+
+int hfr_knn_merge_certify(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, hfr_neighbor* out,
+                          int32_t* unc_list, int32_t* unc_count, int device, void* stream) {
+  return guarded([&] {
+    if (!parts || !out || !unc_list || !unc_count || n_parts <= 0 || nq < 0 || n_neighbors < 1 || n_neighbors > 4)
+      throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_knn_merge_certify(parts, n_parts, nq, n_neighbors, out, unc_list, unc_count, (cudaStream_t)stream);
+  });
+}
+
+int hfr_knn_query_exact(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, const int32_t* unc_list,
+                        const int32_t* unc_count, hfr_neighbor* out, void* stream) {
+  return guarded([&] {
+    if (!k || !queries || !out || !unc_list || !unc_count || nq <= 0 || n_neighbors < 1 || n_neighbors > 4)
+      throw Error(HFR_ERR_INVALID, "bad argument");
+    if (!k->gallery) throw Error(HFR_ERR_STATE, "hfr_knn_query_exact before hfr_knn_set_gallery (NotFittedError)");
+    use_device(k->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    k->locks.ensure((size_t)nq * 4);
+    cuda_check(cudaMemsetAsync(k->locks.p, 0, (size_t)nq * 4, s), "cudaMemsetAsync");
+    launch_knn_exact_listed(queries, (const float*)k->gallery, k->n_local, k->dim, k->row_offset, n_neighbors, unc_list,
+                            unc_count, (int*)k->locks.p, out, k->device, s);
+  });
+}
+
+int hfr_knn_merge_listed(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, const int32_t* unc_list,
+                         const int32_t* unc_count, hfr_neighbor* out, int device, void* stream) {
+  return guarded([&] {
+    if (!parts || !out || !unc_list || !unc_count || n_parts <= 0 || nq < 0 || n_neighbors < 1 || n_neighbors > 4)
+      throw Error(HFR_ERR_INVALID, "bad argument");
+    use_device(device);
+    launch_knn_merge_listed(parts, n_parts, nq, n_neighbors, unc_list, unc_count, out, (cudaStream_t)stream);
   });
 }
 
@@ -1137,7 +1182,7 @@ int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, int n_
                                (cudaStream_t)stream), "cudaMemcpyAsync(H2D)");
   });
   if (rc) return rc;
-  rc = hfr_knn_query(k, (const float*)k->h_q.p, nq, n_neighbors, (hfr_neighbor*)k->h_out.p, stream);
+  rc = knn_query_impl(k, (const float*)k->h_q.p, nq, n_neighbors, (hfr_neighbor*)k->h_out.p, stream, 0);
   if (rc) return rc;
   return guarded([&] {
     cudaStream_t s = (cudaStream_t)stream;

@@ -93,6 +93,9 @@ struct KnnFinalizeParams {
   Neighbor* out;             // [nq][k]
   int* unc_list;             // queries that need the exact pass
   int* counters;             // [0] number of uncertified queries
+  int partial;               // sharded gallery: out is [nq][k + 1] = the k re-scored candidates of THIS shard (always,
+                             // certified or not) + {lower bound on d2 of every row of the shard that was not re-scored,
+                             // index -2}; the certification happens after the exchange, against the GLOBAL k-th distance
 };
 
 // Warp per query.  NC = candidates per bucket record (2 / 4), KEEP = candidates re-scored in fp64.
@@ -187,6 +190,22 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const KnnFinalizePara
   const double gm2 = (double)__ldg(p.gmax2);
   const double E = (p.c_dot * sqrt(qn) * sqrt(gm2) + p.c_norm * gm2) * (1.0 + 1e-9) + 1e-300;
   const bool certified = (t == (double)INFINITY) || (bd[p.k - 1] < qn + t - E);
+  if (p.partial) {
+    if (lane == 0) {
+      Neighbor* o = p.out + row * (p.k + 1);
+      for (int j = 0; j < p.k; ++j) {
+        Neighbor nb;
+        nb.dist2 = bi[j] >= 0 ? bd[j] : (double)INFINITY;
+        nb.index = bi[j] >= 0 ? p.row_offset + bi[j] : -1;
+        o[j] = nb;
+      }
+      Neighbor bnd;
+      bnd.dist2 = (t == (double)INFINITY) ? (double)INFINITY : qn + t - E;
+      bnd.index = -2;
+      o[p.k] = bnd;
+    }
+    return;
+  }
   if (lane == 0) {
     for (int j = 0; j < p.k; ++j) {
       Neighbor nb;
@@ -408,6 +427,94 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(const float* __restric
         o[t].dist2 = md[t];
         o[t].index = mi[t];
       }
+  }
+}
+
+// Sharded gallery, step 2 (after the all-gather of the partial records [P][nq][k + 1], see KnnFinalizeParams::partial):
+// the global k nearest among all shards' re-scored candidates, certified against the smallest of the shards' bounds -
+// every row of every shard that was not re-scored is at least that far away.  A shard that does not hold a query's
+// neighbour therefore costs nothing (certifying per shard sent ~5 % of such queries through the shard's exact pass).
+// Uncertified queries are listed; every rank computes the same list from the same gathered records.
+__global__ void knn_merge_certify_kernel(const Neighbor* __restrict__ parts, int nparts, long long nq, int k,
+                                         Neighbor* __restrict__ out, int* __restrict__ unc_list, int* __restrict__ unc_count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  double md[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  long long mi[4] = {-1, -1, -1, -1};
+  double bound = INFINITY;
+  for (int p = 0; p < nparts; ++p) {
+    const Neighbor* rec = parts + ((size_t)p * nq + i) * (k + 1);
+    bound = fmin(bound, rec[k].dist2);
+    for (int e = 0; e < k; ++e) {
+      double cd = rec[e].dist2;
+      long long ci = rec[e].index;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (ci >= 0 && (mi[t] < 0 || cd < md[t] || (cd == md[t] && ci < mi[t]))) {
+          const double td = md[t];
+          const long long ti = mi[t];
+          md[t] = cd;
+          mi[t] = ci;
+          cd = td;
+          ci = ti;
+        }
+      }
+    }
+  }
+  for (int t = 0; t < k; ++t) {
+    Neighbor nb;
+    nb.dist2 = md[t];
+    nb.index = mi[t];
+    out[i * k + t] = nb;
+  }
+  const bool certified = (bound == (double)INFINITY) || (md[k - 1] < bound);
+  if (!certified) unc_list[atomicAdd(unc_count, 1)] = (int)i;
+}
+
+// Sharded gallery, step 3 (only when step 2 listed queries): the listed rows of a [nq][k] result start empty ...
+__global__ void knn_clear_listed_kernel(const int* __restrict__ unc_list, const int* __restrict__ unc_count, int k,
+                                        Neighbor* __restrict__ out) {
+  const int nu = unc_count[0];
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu * k; u += gridDim.x * blockDim.x) {
+    Neighbor nb;
+    nb.dist2 = INFINITY;
+    nb.index = -1;
+    out[(long long)unc_list[u / k] * k + u % k] = nb;
+  }
+}
+// ... knn_exact_kernel + knn_rescore_kernel fill them from the local shard, and after the second all-gather the listed
+// rows of the result are replaced by the merge of the shards' exact answers.
+__global__ void knn_merge_listed_kernel(const Neighbor* __restrict__ parts, int nparts, long long nq, int k,
+                                        const int* __restrict__ unc_list, const int* __restrict__ unc_count,
+                                        Neighbor* __restrict__ out) {
+  const int nu = unc_count[0];
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+    const long long i = unc_list[u];
+    double md[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    long long mi[4] = {-1, -1, -1, -1};
+    for (int p = 0; p < nparts; ++p)
+      for (int e = 0; e < k; ++e) {
+        const Neighbor nb = parts[((size_t)p * nq + i) * k + e];
+        double cd = nb.dist2;
+        long long ci = nb.index;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (ci >= 0 && (mi[t] < 0 || cd < md[t] || (cd == md[t] && ci < mi[t]))) {
+            const double td = md[t];
+            const long long ti = mi[t];
+            md[t] = cd;
+            mi[t] = ci;
+            cd = td;
+            ci = ti;
+          }
+        }
+      }
+    for (int t = 0; t < k; ++t) {
+      Neighbor nb;
+      nb.dist2 = md[t];
+      nb.index = mi[t];
+      out[i * k + t] = nb;
+    }
   }
 }
 

@@ -898,6 +898,14 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
 #undef HFR_KNN_LAUNCH
 }
 
+static void configure_knn_exact(int device) {
+  static std::atomic<bool> configured[64];
+  if (!configured[device].load()) {
+    cuda_check(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnExactSmem)),
+               "cudaFuncSetAttribute(knn exact smem)");
+    configured[device].store(true);
+  }
+}
 void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s) {
   if (a.nq <= 0) return;
   if (a.k < 1 || a.k > 4) throw Error(-1, "k-NN: k must be 1..4");
@@ -912,23 +920,45 @@ void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s) {
   p.c_dot = 2.0 * (2.0 * u + u * u + c_acc) + 1.0 / 8388608;
   p.c_norm = (double)(a.d + 4) / 16777216.0;
   p.gmax2 = a.gmax2;
-  p.out = (Neighbor*)a.out; p.unc_list = a.unc_list; p.counters = a.counters;
+  p.out = (Neighbor*)a.out; p.unc_list = a.unc_list; p.counters = a.counters; p.partial = a.partial;
   const unsigned grid = (unsigned)((a.nq + 7) / 8);
   if (a.cand == 2) knn_finalize_kernel<2, 4><<<grid, 256, 0, s>>>(p);
   else knn_finalize_kernel<4, 8><<<grid, 256, 0, s>>>(p);
   HFR_LAUNCH_CHECK("knn_finalize");
+  if (a.partial) return;   // sharded gallery: certification and the exact pass follow the exchange
   // exact pass over the queries the bound could not certify (usually none: the kernel reads the count and returns)
-  static std::atomic<bool> configured[64];
-  if (!configured[device].load()) {
-    cuda_check(cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KnnExactSmem)),
-               "cudaFuncSetAttribute(knn exact smem)");
-    configured[device].store(true);
-  }
+  configure_knn_exact(device);
   knn_exact_kernel<<<(unsigned)(2 * device_sm_count(device)), 256, sizeof(KnnExactSmem), s>>>(
       a.q, a.g, (long long)a.n, a.d, (long long)a.row_offset, a.k, a.unc_list, a.counters, a.locks, (Neighbor*)a.out);
   HFR_LAUNCH_CHECK("knn_exact");
   knn_rescore_kernel<<<64, 256, 0, s>>>(a.q, a.g, a.d, (long long)a.row_offset, a.k, a.unc_list, a.counters, (Neighbor*)a.out);
   HFR_LAUNCH_CHECK("knn_rescore");
+}
+
+void launch_knn_merge_certify(const void* parts, int n_parts, int64_t nq, int k, void* out, int* unc_list, int* unc_count,
+                              cudaStream_t s) {
+  cuda_check(cudaMemsetAsync(unc_count, 0, 4, s), "cudaMemsetAsync");
+  if (nq <= 0) return;
+  knn_merge_certify_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>((const Neighbor*)parts, n_parts, (long long)nq, k,
+                                                                        (Neighbor*)out, unc_list, unc_count);
+  HFR_LAUNCH_CHECK("knn_merge_certify");
+}
+void launch_knn_exact_listed(const float* q, const float* g, int64_t n, int d, int64_t row_offset, int k, const int* unc_list,
+                             const int* unc_count, int* locks, void* out, int device, cudaStream_t s) {
+  configure_knn_exact(device);
+  knn_clear_listed_kernel<<<64, 256, 0, s>>>(unc_list, unc_count, k, (Neighbor*)out);
+  HFR_LAUNCH_CHECK("knn_clear_listed");
+  knn_exact_kernel<<<(unsigned)(2 * device_sm_count(device)), 256, sizeof(KnnExactSmem), s>>>(
+      q, g, (long long)n, d, (long long)row_offset, k, unc_list, unc_count, locks, (Neighbor*)out);
+  HFR_LAUNCH_CHECK("knn_exact");
+  knn_rescore_kernel<<<64, 256, 0, s>>>(q, g, d, (long long)row_offset, k, unc_list, unc_count, (Neighbor*)out);
+  HFR_LAUNCH_CHECK("knn_rescore");
+}
+void launch_knn_merge_listed(const void* parts, int n_parts, int64_t nq, int k, const int* unc_list, const int* unc_count,
+                             void* out, cudaStream_t s) {
+  knn_merge_listed_kernel<<<64, 256, 0, s>>>((const Neighbor*)parts, n_parts, (long long)nq, k, unc_list, unc_count,
+                                             (Neighbor*)out);
+  HFR_LAUNCH_CHECK("knn_merge_listed");
 }
 
 void launch_knn_merge(const void* parts, int n_parts, int64_t nq, int k, void* out, cudaStream_t s) {

@@ -178,8 +178,17 @@ struct KnnFinalizeArgs {
   int* unc_list;
   int* counters;
   int* locks;
+  int partial;   // 1: out is [nq][k + 1] candidates + bound record, no certification / exact pass (sharded gallery)
 };
 void launch_knn_finalize(const KnnFinalizeArgs& a, int device, cudaStream_t s);
+// sharded gallery (knn.cuh): global merge + certification of gathered partial records; exact pass over listed queries;
+// merge of the gathered exact answers into the listed rows
+void launch_knn_merge_certify(const void* parts, int n_parts, int64_t nq, int k, void* out, int* unc_list, int* unc_count,
+                              cudaStream_t s);
+void launch_knn_exact_listed(const float* q, const float* g, int64_t n, int d, int64_t row_offset, int k, const int* unc_list,
+                             const int* unc_count, int* locks, void* out, int device, cudaStream_t s);
+void launch_knn_merge_listed(const void* parts, int n_parts, int64_t nq, int k, const int* unc_list, const int* unc_count,
+                             void* out, cudaStream_t s);
 // pairwise euclidean distances (+ optional album age penalty), fp32 direct differences; y == x: the diagonal is forced
 // to exact zeros
 void launch_pairwise_dist(const float* x, const float* y, int64_t n, int64_t m, int d, const float* year_x,

@@ -168,6 +168,25 @@ int hfr_knn_query_host(hfr_knn* k, const float* queries_host, int64_t nq, int n_
  * into the global n_neighbors nearest per query: ascending (dist2, index), ties -> lowest index. */
 int hfr_knn_merge(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, hfr_neighbor* out, int device,
                   void* stream);
+/* Row-sharded gallery, exact and shard-independent (what KNeighborsClassifier(sharded=True) runs; the merge above only
+ * combines finished per-shard answers).  Certifying per shard would send every query whose neighbour lives in ANOTHER
+ * shard through this shard's fp64 pass; instead
+ *   1. hfr_knn_query_partial: out [nq][n_neighbors + 1] = the shard's re-scored candidates (ascending, (inf,-1) padded)
+ *      followed by one record {lower bound on dist2 of every row of the shard that was not re-scored, index -2};
+ *   2. all-gather the records ([n_parts][nq][n_neighbors + 1], one collective), hfr_knn_merge_certify: global nearest of
+ *      all candidates into out [nq][n_neighbors]; a query whose n_neighbors-th distance is not strictly below the
+ *      smallest bound is appended to unc_list (device int32 [nq]); *unc_count (device int32) receives the count -
+ *      identical on every rank, so every rank takes the same branch;
+ *   3. only if the count is not zero: hfr_knn_query_exact fills the listed rows of a local [nq][n_neighbors] array
+ *      with the shard's fp64 brute-force answer, the arrays are all-gathered and hfr_knn_merge_listed overwrites the
+ *      listed rows of `out`. */
+int hfr_knn_query_partial(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, hfr_neighbor* out, void* stream);
+int hfr_knn_merge_certify(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, hfr_neighbor* out,
+                          int32_t* unc_list, int32_t* unc_count, int device, void* stream);
+int hfr_knn_query_exact(hfr_knn* k, const float* queries, int64_t nq, int n_neighbors, const int32_t* unc_list,
+                        const int32_t* unc_count, hfr_neighbor* out, void* stream);
+int hfr_knn_merge_listed(const hfr_neighbor* parts, int n_parts, int64_t nq, int n_neighbors, const int32_t* unc_list,
+                         const int32_t* unc_count, hfr_neighbor* out, int device, void* stream);
 /* Counters of the last hfr_knn_query on this handle (synchronises its stream): queries certified by the error bound /
  * queries re-scored against the whole shard in fp64. */
 int hfr_knn_stats(hfr_knn* k, int64_t* certified, int64_t* rescored);

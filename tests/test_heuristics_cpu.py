@@ -30,14 +30,30 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
                 seen.add(r["ID"])
                 names.append(r["Kernel Name"])
     seq = []            # one entry per launch of an eager step, in order (see tools/traffic_from_launches.py)
-    for L in layers:
+    sub_outs = {L["out"] for L in layers if L["kind"] == "subsample"}
+    skip = False
+    for i, L in enumerate(layers):
         if L["kind"] == "subsample" and all(U["kind"] == "pw" for U in layers if U["in"] == L["out"]):
             continue    # bypassed: its consumers gather through the im2col map
-        seq += [L, L] if L["kind"] == "stem" else [L]
+        if skip:        # the 'reduce' half of a gemm_pair_kernel launch
+            skip = False
+            continue
+        pair = None
+        if L["kind"] == "pw" and i + 1 < len(layers) and L["in"] not in sub_outs:
+            N = layers[i + 1]   # launch.cu: gemm_pair_eligible
+            if (N["kind"] == "pw" and N["in"] == L["out"] and N.get("in2", -1) < 0 and L["cout"] % 128 == 0
+                    and N["cout"] in (64, 128, 256) and (L["cin"] + 63) // 64 <= 4):
+                pair, skip = N, True
+        seq += [(L, None), (L, None)] if L["kind"] == "stem" else [(L, pair)]
     names = names[:len(seq)]
-    assert len(names) == len(seq) == 56
-    batch, checked = 256, 0
-    for L, name in zip(seq, names):
+    assert len(names) == len(seq) == 48
+    batch, checked, pairs = 256, 0, 0
+    for (L, pair), name in zip(seq, names):
+        if pair is not None:                                   # <T, N2, NBUF, PF>
+            assert "gemm_pair_kernel" in name, (L["name"], name)
+            assert int(name.split("<")[1].split(">")[0].replace(" ", "").split(",")[1]) == pair["cout"]
+            pairs += 1
+            continue
         if "gemm_tc_kernel" not in name:
             continue
         targs = name.split("<")[1].split(">")[0].replace(" ", "").split(",")      # <T, BLOCK_N, EPI, AMODE, CTAS>
@@ -46,7 +62,7 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
         M, N, K = batch * L["hw_out"][0] * L["hw_out"][1], L["cout"], L["cin"] * max(taps, 1)
         assert tile_choice(M, N, K, taps) == (ctas_seen, bn_seen), (L["name"], M, N, K, taps)
         checked += 1
-    assert checked == 49
+    assert pairs == 8 and checked == 49 - 16
 
 
 def test_tile_choice_policy_edges():

@@ -176,6 +176,79 @@ def test_sklearn_protocol(tmp_path):
         hfr.KNeighborsClassifier().predict(X)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_sharded_protocol_certifies_globally_and_stays_exact(precision):
+    """The row-sharded protocol of include/hfr.h on one GPU (4 handles stand in for 4 ranks, torch.stack for the
+    all-gather): hfr_knn_query_partial -> hfr_knn_merge_certify -> (listed queries only) hfr_knn_query_exact ->
+    hfr_knn_merge_listed.  Planted queries are certified after the exchange although three of the four shards do not hold
+    their neighbour (per-shard certification sent those to the shards' fp64 passes: 7x slower at 2 GPUs); random queries
+    and a query with six near-duplicate neighbours are listed, and every result equals the single-gallery answer."""
+    import ctypes as C
+    from hse_facerec_tf_b200._lib import check, lib, PREC
+    n, d = 20000, 512
+    g, q, _ = make_problem(n, 400, d, seed=21)         # planted queries (_ = the rows they were planted next to)
+    rs = np.random.RandomState(5)
+    r0 = next(r for r in range(300, n - 6) if not np.isin(np.arange(r, r + 6), _).any())   # rows no planted query uses
+    v = g[r0].copy()
+    g[r0:r0 + 6] = v + 1e-5 * rs.randn(6, d).astype(np.float32)
+    qr = rs.randn(200, d).astype(np.float32)
+    qr /= np.linalg.norm(qr, axis=1, keepdims=True)
+    qr[1] = v
+    bounds = [0, 3, 5000, 12000, n]
+    shards = []
+    for a0, b0 in zip(bounds[:-1], bounds[1:]):
+        gt = torch.from_numpy(g[a0:b0]).cuda()
+        h = C.c_void_p()
+        check(lib.hfr_knn_create(0, d, PREC[precision], C.byref(h)))
+        check(lib.hfr_knn_set_gallery(h, gt.data_ptr(), b0 - a0, a0, None))
+        shards.append((gt, h))
+
+    def sharded_query(queries, k):
+        qt = torch.from_numpy(queries).cuda()
+        nq = len(queries)
+        parts = []
+        for _, h in shards:
+            o = torch.empty((nq, k + 1, 2), dtype=torch.int64, device="cuda")
+            check(lib.hfr_knn_query_partial(h, qt.data_ptr(), nq, k, o.data_ptr(), None))
+            parts.append(o)
+        parts = torch.stack(parts).contiguous()
+        out = torch.empty((nq, k, 2), dtype=torch.int64, device="cuda")
+        unc = torch.empty((nq + 1,), dtype=torch.int32, device="cuda")
+        check(lib.hfr_knn_merge_certify(parts.data_ptr(), len(shards), nq, k, out.data_ptr(), unc[1:].data_ptr(),
+                                        unc.data_ptr(), 0, None))
+        n_unc = int(unc[0].item())
+        if n_unc:
+            locs = []
+            for _, h in shards:
+                loc = torch.empty((nq, k, 2), dtype=torch.int64, device="cuda")
+                check(lib.hfr_knn_query_exact(h, qt.data_ptr(), nq, k, unc[1:].data_ptr(), unc.data_ptr(), loc.data_ptr(), None))
+                locs.append(loc)
+            parts2 = torch.stack(locs).contiguous()
+            check(lib.hfr_knn_merge_listed(parts2.data_ptr(), len(shards), nq, k, unc[1:].data_ptr(), unc.data_ptr(),
+                                           out.data_ptr(), 0, None))
+        torch.cuda.synchronize()
+        rec = out.cpu().numpy()
+        listed = set(unc[1:1 + n_unc].cpu().numpy().tolist())
+        return np.ascontiguousarray(rec[:, :, 0]).view(np.float64), rec[:, :, 1], listed
+
+    for k in (1, 3):
+        whole = hfr.KNeighborsClassifier(n_neighbors=k, precision=precision).fit(g, np.arange(n))
+        d2, ind, listed = sharded_query(q, k)
+        d_ref, i_ref = whole.kneighbors(q)
+        np.testing.assert_array_equal(ind, i_ref)
+        np.testing.assert_array_equal(np.sqrt(d2), d_ref)
+        if k == 1:
+            assert not listed, listed                    # planted neighbours: certified globally
+        d2, ind, listed = sharded_query(qr, k)
+        d_ref, i_ref = whole.kneighbors(qr)
+        np.testing.assert_array_equal(ind, i_ref)
+        np.testing.assert_array_equal(np.sqrt(d2), d_ref)
+        assert 1 in listed                               # six near-duplicates, four re-scored: cannot be certified
+        assert r0 <= ind[1, 0] < r0 + 6
+    for _, h in shards:
+        lib.hfr_knn_free(h)
+
+
 def test_merge_of_shards_equals_single_gallery():
     """Gallery row-sharded over 4 handles on one GPU + hfr_knn_merge == one handle over the whole gallery (k = 1 and 3,
     duplicates across shards, a shard smaller than k)."""

@@ -48,6 +48,27 @@ def main():
     np.testing.assert_array_equal(d3s, d3w)
     assert i3s[0].tolist()[:2] == [5, 40_000]
     np.testing.assert_array_equal(sh3.predict(q), wh3.predict(q))
+    # global certification: the planted queries above are all certified after the exchange although most shards do not
+    # hold their neighbour; six near-duplicates inside one shard cannot be (only four candidates are re-scored), so
+    # that query - and whatever random queries fail the bound - take the fp64 passes and the second exchange
+    cert, unc = sharded.query_stats()
+    assert unc == 0 and cert == nq, (cert, unc)
+    g2 = g.copy()
+    v = g2[100].copy()
+    g2[100:106] = v + 1e-5 * rs.randn(6, d).astype(np.float32)
+    qr = rs.randn(300, d).astype(np.float32)
+    qr /= np.linalg.norm(qr, axis=1, keepdims=True)
+    qr[1] = v
+    for k in (1, 3):
+        sh = hfr.KNeighborsClassifier(k, 2, device=dev, precision="bf16", sharded=True).fit(g2[a:b], y[a:b])
+        wh = hfr.KNeighborsClassifier(k, 2, device=dev, precision="bf16").fit(g2, y)
+        d_rs, i_rs = sh.kneighbors(qr)
+        cert, unc = sh.query_stats()
+        d_rw, i_rw = wh.kneighbors(qr)
+        np.testing.assert_array_equal(i_rs, i_rw)
+        np.testing.assert_array_equal(d_rs, d_rw)
+        assert unc >= 1 and cert + unc == len(qr), (cert, unc)
+        assert 100 <= i_rs[1, 0] < 106
     # ---- extraction: batch sharded, no collective on the data path; gather only to compare
     pb = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "age_gender_quantized.pb")
     tfi = hfr.TensorFlowInference(pb, "input_1:0", "global_pooling/Mean:0", device=dev, precision="bf16", input_hw=192)

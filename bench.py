@@ -178,9 +178,9 @@ def plan_work(plan, es):
         out_b = ho * wo * L["cout"] * (4 if kind in ("gap", "fc", "head") else es)
         if kind in ("fc", "head"):
             in_b, out_b = L["cin"] * 4, L["cout"] * 4
-        if L["in2"] >= 0:
-            in_b += ho * wo * L["cout"] * es
-        rows.append(dict(kind=kind, name=L["name"], flops=flops, bytes=float(in_b + out_b), out_bytes=float(out_b)))
+        res_b = ho * wo * L["cout"] * es if L["in2"] >= 0 else 0
+        rows.append(dict(kind=kind, name=L["name"], flops=flops, bytes=float(in_b + res_b + out_b), out_bytes=float(out_b),
+                         in_bytes=float(in_b), res_bytes=float(res_b), out=L["out"], in2=L["in2"]))
     return rows
 
 
@@ -305,11 +305,23 @@ def bench_network(workload, precision, args, rank, world, dev):
     per_step = [t / max(lsteps, 1) for t in lms]
     merged = []
     i = 0
+    absorbed = None
     while i < len(work):
         w, t = dict(work[i]), per_step[i]
         if t < 0:
-            i += 1      # nothing launched (the library reports -1): a bypassed gather
+            # nothing launched (the library reports -1): a bypassed gather, or an 'increase' 1x1 convolution that the next
+            # layer (the projection shortcut it is the residual of) absorbed by K-concatenation (api.cu: plan_kcat)
+            if (w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] >= 0
+                    and work[i + 1]["in2"] == w["out"]):
+                absorbed = w
+            i += 1
             continue
+        if absorbed is not None:
+            # one GEMM over [x_mid | x_in]: both layers' flops; bytes = both inputs + the output, no residual tensor
+            w["name"] = absorbed["name"] + " (+) " + w["name"]
+            w["flops"] += absorbed["flops"]
+            w["bytes"] += absorbed["in_bytes"] - w["res_bytes"]
+            absorbed = None
         if w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 0:
             # gemm_pair_kernel: this 1x1 convolution and the next one in ONE launch.  The launch's algorithmic work is both
             # layers' flops and this layer's bytes plus the second layer's OUTPUT only (its input never leaves the SM)

@@ -164,6 +164,10 @@ struct LayerDev {
   void* w = nullptr;      // kernel-ready weights
   void* w_win = nullptr;  // conv_window_kernel layout, when the layer qualifies
   float* bias = nullptr;
+  // K-concatenation candidate (kcat_candidate): [cout][K_prev + K] = the previous layer's weights and this layer's side
+  // by side, and the sum of the two biases
+  void* w_cat = nullptr;
+  float* bias_cat = nullptr;
 };
 
 struct GraphKey {
@@ -288,6 +292,42 @@ struct hfr_model {
     }
   }
 
+  // First block of a ResNet stage:  y = ReLU(increase(x_mid) + projection(x_in)), stated by the plan as a 1x1 convolution
+  // without activation ('increase_bn') whose output is the residual input of the next 1x1 convolution (the projection
+  // shortcut).  Both are linear, so they are ONE GEMM over the concatenated reduction dimension,
+  // [x_mid | x_in] [W_inc | W_proj]^T + (b_inc + b_proj): the 'increase' tensor is never written or re-read (411 MB each
+  // way in stage 2 at batch 256) and a launch disappears; the sum is accumulated in fp32 instead of being rounded to
+  // the storage type in between.  kcat_of[j] = i: layer j absorbs layer i.  Off when every activation has to exist.
+  std::vector<int> kcat_of;
+  std::vector<char> kcat_skip;
+  bool kcat_candidate(size_t i) const {   // pattern only (what upload_weights prepares), independent of the run mode
+    if (i + 1 >= plan.layers.size() || precision == HFR_FP32) return false;
+    const Layer& A = plan.layers[i];
+    const Layer& B = plan.layers[i + 1];
+    if (A.kind != L_PW || B.kind != L_PW || A.act != A_NONE || A.in2 >= 0 || B.in2 != A.out || B.in == A.out) return false;
+    if (A.cout != B.cout || A.Ho != B.Ho || A.Wo != B.Wo || A.bias.empty() != B.bias.empty()) return false;
+    const int bk = 128 / (int)elt_size(precision);
+    if (A.cin % bk || B.cin % bk) return false;
+    for (size_t li = 0; li < plan.layers.size(); ++li) {      // nobody else reads the intermediate
+      if (li == i + 1) continue;
+      if (plan.layers[li].in == A.out || plan.layers[li].in2 == A.out) return false;
+    }
+    for (int o : plan.outputs) if (o == A.out) return false;
+    return true;
+  }
+  void plan_kcat() {
+    const size_t n = plan.layers.size();
+    kcat_of.assign(n, -1);
+    kcat_skip.assign(n, 0);
+    const char* e = getenv("HFR_KCAT");
+    if (keep_all || (e && atoi(e) == 0)) return;
+    for (size_t i = 0; i + 1 < n; ++i) {
+      if (!kcat_candidate(i) || gather_of[i] >= 0 || dev.size() != n || dev[i + 1].w_cat == nullptr) continue;
+      kcat_of[i + 1] = (int)i;
+      kcat_skip[i] = 1;
+    }
+  }
+
   // The dense tail (a hidden Dense layer on the pooled vector followed by the output heads) runs as one launch of
   // dense_heads_kernel when it has that shape: layers [head_first, head_first + head_count) of the plan.
   int head_first = -1, head_count = 0;
@@ -324,14 +364,20 @@ struct hfr_model {
     val_off.assign((size_t)nv, 0);
     val_bytes.assign((size_t)nv, 0);
     plan_gather_bypass();
+    plan_kcat();
     // a bypassing layer reads the gather's INPUT: that value lives until its last bypassing reader
     std::vector<int> last_use((size_t)nv);
     for (int v = 0; v < nv; ++v) last_use[(size_t)v] = plan.values[(size_t)v].last_use;
-    for (size_t li = 0; li < plan.layers.size(); ++li)
+    for (size_t li = 0; li < plan.layers.size(); ++li) {
       if (gather_of[li] >= 0) {
         const int src = plan.layers[(size_t)gather_of[li]].in;
         if (src > 0 && last_use[(size_t)src] < (int)li) last_use[(size_t)src] = (int)li;
       }
+      if (kcat_of[li] >= 0) {   // the absorbing layer reads the absorbed layer's input
+        const int src = plan.layers[(size_t)kcat_of[li]].in;
+        if (src > 0 && last_use[(size_t)src] < (int)li) last_use[(size_t)src] = (int)li;
+      }
+    }
     struct Block { size_t off, size; };
     std::vector<Block> free_list;
     size_t top = 0;
@@ -363,15 +409,19 @@ struct hfr_model {
     };
     for (int li = 0; li < (int)plan.layers.size(); ++li) {
       const Layer& L = plan.layers[(size_t)li];
-      if (skip_layer[(size_t)li]) {  // never materialised; its input may end its life here unless a bypassing layer reads it
+      if (skip_layer[(size_t)li] || kcat_skip[(size_t)li]) {  // never materialised; its input may end its life here unless a later layer reads it in its place
         if (L.in > 0 && last_use[(size_t)L.in] == li) release(val_off[(size_t)L.in], val_bytes[(size_t)L.in]);
         continue;
       }
       val_bytes[(size_t)L.out] = value_image_bytes(L.out);
       val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
       if (keep_all) continue;
-      int ins[2] = {L.in, L.in2};
+      int ins[3] = {L.in, L.in2, -1};
       if (gather_of[(size_t)li] >= 0) ins[0] = plan.layers[(size_t)gather_of[(size_t)li]].in;
+      if (kcat_of[(size_t)li] >= 0) {   // no residual tensor exists; the absorbed layer's input is read instead
+        ins[1] = -1;
+        ins[2] = plan.layers[(size_t)kcat_of[(size_t)li]].in;
+      }
       for (int v : ins) {
         if (v <= 0) continue;  // value 0 is the caller's input
         if (last_use[(size_t)v] == li) release(val_off[(size_t)v], val_bytes[(size_t)v]);
@@ -407,6 +457,33 @@ struct hfr_model {
         d.w = upload(L.w.data(), L.w.size() * 4);
       }
     }
+    for (size_t i = 0; i + 1 < plan.layers.size(); ++i) {
+      if (!kcat_candidate(i)) continue;
+      const Layer& A = plan.layers[i];
+      const Layer& B = plan.layers[i + 1];
+      const size_t N = (size_t)A.cout, Ka = (size_t)A.cin, Kb = (size_t)B.cin;
+      if (A.w.size() != N * Ka || B.w.size() != N * Kb) continue;
+      std::vector<float> cat(N * (Ka + Kb));
+      for (size_t n = 0; n < N; ++n) {
+        std::copy(A.w.begin() + (long)(n * Ka), A.w.begin() + (long)((n + 1) * Ka), cat.begin() + (long)(n * (Ka + Kb)));
+        std::copy(B.w.begin() + (long)(n * Kb), B.w.begin() + (long)((n + 1) * Kb), cat.begin() + (long)(n * (Ka + Kb) + Ka));
+      }
+      LayerDev& d = dev[i + 1];
+      if (precision == HFR_BF16) {
+        std::vector<uint16_t> h(cat.size());
+        for (size_t j = 0; j < h.size(); ++j) h[j] = f32_to_bf16(cat[j]);
+        d.w_cat = upload(h.data(), h.size() * 2);
+      } else {
+        for (float& v : cat) v = f32_to_tf32(v);
+        d.w_cat = upload(cat.data(), cat.size() * 4);
+      }
+      if (!A.bias.empty()) {
+        std::vector<float> bsum(N);
+        for (size_t n = 0; n < N; ++n) bsum[n] = A.bias[n] + B.bias[n];
+        d.bias_cat = (float*)upload(bsum.data(), N * 4);
+      }
+    }
+    plan_arena();   // the K-concatenation plan depends on the uploaded weights
   }
 
   bool feeds_tensor_core(int v) const {
@@ -551,11 +628,20 @@ struct hfr_model {
           break;
         }
         case L_PW: {
+          if (kcat_skip[i]) { launched[i] = 0; break; }   // absorbed by the next layer's GEMM (plan_kcat)
+          // K-concatenation: this GEMM also reduces over the absorbed layer's input with its weights, no residual
+          const bool kcat = kcat_of[i] >= 0;
+          const Layer* KA = kcat ? &plan.layers[(size_t)kcat_of[i]] : nullptr;
+          const void* w_use = kcat ? d.w_cat : d.w;
+          const float* bias_use = kcat ? d.bias_cat : d.bias;
+          const void* res_use = kcat ? nullptr : (L.in2 >= 0 ? vptr(L.in2) : nullptr);
+          const void* a0_use = kcat ? (KA->in == 0 ? x : vptr(KA->in)) : nullptr;
+          const int k0_use = kcat ? KA->cin : 0;
           if (gather_of[i] >= 0) {  // strided 1x1: im2col-gathered A operand, no materialised subsample
             const Layer& S = plan.layers[(size_t)gather_of[i]];
             ConvArgs a;
-            a.x = S.in == 0 ? x : vptr(S.in); a.w = d.w; a.bias = d.bias;
-            a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
+            a.x = S.in == 0 ? x : vptr(S.in); a.w = w_use; a.bias = bias_use;
+            a.residual = res_use; a.a0 = a0_use; a.K0 = k0_use;
             a.y = out; a.B = batch; a.H = S.H; a.W = S.W; a.cin = L.cin; a.Ho = L.Ho; a.Wo = L.Wo; a.cout = L.cout;
             a.kh = 1; a.kw = 1; a.stride = S.stride; a.pad_t = 0; a.pad_l = 0; a.dil = 1;
             a.act = act; a.round_tf32 = round_out;
@@ -563,8 +649,8 @@ struct hfr_model {
             break;
           }
           GemmArgs a;
-          a.a = in; a.b = d.w; a.bias = d.bias;
-          a.residual = L.in2 >= 0 ? vptr(L.in2) : nullptr;
+          a.a = in; a.b = w_use; a.bias = bias_use;
+          a.residual = res_use; a.a0 = a0_use; a.K0 = k0_use;
           a.y = out; a.M = (int64_t)batch * L.Ho * L.Wo; a.N = L.cout; a.K = L.cin;
           a.act = act; a.round_tf32 = round_out;
           // the next layer is a plain 1x1 convolution over this layer's output (the seam between two bottleneck blocks):

@@ -44,6 +44,7 @@ struct PairParams {
   int act1, round1;
   const float* bias2;    // [N2] or nullptr
   int act2, round2;
+  int kb_split;          // the first kb_split k-blocks of A come from the concatenated operand A0 (tmA0), see GemmParams
   int na;                // A buffers (units in flight): 2 when K1 <= 2 k-blocks, else 1
   int stages;            // 16 KB slots of the weight ring (what is left of the shared memory, <= 8)
 };
@@ -66,7 +67,8 @@ template <typename T, int N2, int NBUF, int PF>
 __global__ void __launch_bounds__(384, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmD1, const __grid_constant__ CUtensorMap tmR,
-                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2, const PairParams p) {
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2,
+                 const __grid_constant__ CUtensorMap tmA0, const PairParams p) {
   using TR = GemmTraits<T>;
   constexpr int SLOT = PairSmem::kSlotBytes;
   constexpr int BK = TR::BK;
@@ -115,6 +117,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB2);
     tma_prefetch_desc(&tmD2);
     if (use_res) tma_prefetch_desc(&tmR);
+    if (p.kb_split > 0) tma_prefetch_desc(&tmA0);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -197,8 +200,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(aempty_bar(ab), (uint32_t)((ul / NA) & 1) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(afull_bar(ab), a_bytes);
-        for (int kb = 0; kb < num_kb; ++kb)
-          tma_load_2d(sA + (uint32_t)ab * a_bytes + kb * SLOT, &tmA, afull_bar(ab), kb * BK, mb * 128);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (kb < p.kb_split) tma_load_2d(sA + (uint32_t)ab * a_bytes + kb * SLOT, &tmA0, afull_bar(ab), kb * BK, mb * 128);
+          else tma_load_2d(sA + (uint32_t)ab * a_bytes + kb * SLOT, &tmA, afull_bar(ab), (kb - p.kb_split) * BK, mb * 128);
+        }
       }
       __syncwarp();
     }

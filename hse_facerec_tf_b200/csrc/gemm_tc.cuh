@@ -54,6 +54,11 @@ struct GemmParams {
   // AMODE_STEM16 (stem convolution after space-to-depth: 16 channels = 32 bytes per pixel, one MMA K-step per tap):
   // k-block = 4 taps; taps are (a, b) over a conv_kh x conv_kw window, stride 1, no padding.  B = [taps][N][16].
   int conv_kh, conv_taps;
+  // K-concatenated A operand (AMODE_2D / AMODE_IM2COL): the first kb_split k-blocks come from a second, plain 2-D matrix
+  // A0[M, kb_split * BK] (tensor map tmA0), the rest from the main operand; B = [N, K0 + K] holds both weight matrices side
+  // by side.  ResNet's first block of a stage:  ReLU(increase(x_mid) + projection(x_in))  is ONE accumulation, the
+  // 'increase' output is never written or re-read.
+  int kb_split;
 };
 
 template <typename T>
@@ -88,7 +93,8 @@ struct GemmSmem {
 template <typename T, int BLOCK_N, int EPI, int AMODE, int CTAS = 1>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmA0, const GemmParams p) {
   using TR = GemmTraits<T>;
   using SM = GemmSmem<BLOCK_N, EPI, CTAS>;
   constexpr int STAGES = SM::kStages;
@@ -123,6 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmD);
     if (EPI == EPI_STORE && p.residual != nullptr) tma_prefetch_desc(&tmR);
+    if (p.kb_split > 0) tma_prefetch_desc(&tmA0);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -143,9 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_launch_dependents();  // the next kernel may run its prologue now ...
   pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
 
-  const int num_kb = (AMODE == AMODE_IM2COL)  ? p.conv_kw * p.conv_kw * p.conv_cblocks
+  const int num_kb = (AMODE == AMODE_IM2COL)  ? p.conv_kw * p.conv_kw * p.conv_cblocks + p.kb_split
                      : (AMODE == AMODE_STEM16) ? (p.conv_taps + 3) / 4
-                                               : (p.K + BK - 1) / BK;
+                                               : (p.K + BK - 1) / BK;   // AMODE_2D: p.K is the total (K0 + K)
   const int units_n = (p.num_n_blocks + p.n_blocks_per_unit - 1) / p.n_blocks_per_unit;
 
   // unit -> (m block, first n block, n block count).  STORE: n fastest (neighbouring CTAs share the A tile in L2).
@@ -188,17 +195,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (elect_one()) {
               const uint32_t fb = full_bar0 + 8u * stage;
               if (cta_rank == 0) mbar_expect_tx(full_bar(stage), SM::kStageBytes * CTAS);
+              const bool prefix = (AMODE != AMODE_STEM16) && kb < p.kb_split;   // k-block of the concatenated A0 operand
+              [[maybe_unused]] const int kb2 = kb - p.kb_split;
               if constexpr (CTAS == 2) {
                 static_assert(CTAS == 1 || AMODE != AMODE_STEM16, "pair mode: 2-D and im2col A operands only");
-                if (AMODE == AMODE_IM2COL)
+                if (prefix)
+                  tma_load_2d_pair(sA + stage * SM::kABytes, &tmA0, fb, kb * BK, mb * 128);
+                else if (AMODE == AMODE_IM2COL)
                   tma_load_im2col_4d_pair(sA + stage * SM::kABytes, &tmA, fb, cb * BK,
                                           im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
                                           (uint16_t)(tap_s * p.conv_dil), (uint16_t)(tap_r * p.conv_dil));
                 else
-                  tma_load_2d_pair(sA + stage * SM::kABytes, &tmA, fb, kb * BK, mb * 128);
+                  tma_load_2d_pair(sA + stage * SM::kABytes, &tmA, fb, kb2 * BK, mb * 128);
                 // this CTA's half of the tile's B rows
                 tma_load_2d_pair(sB + stage * SM::kBBytes, &tmB, fb, kb * BK,
                                  nb * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+              } else if (prefix) {
+                tma_load_2d(sA + stage * SM::kABytes, &tmA0, full_bar(stage), kb * BK, mb * 128);
               } else if (AMODE == AMODE_IM2COL) {
                 tma_load_im2col_4d(sA + stage * SM::kABytes, &tmA, full_bar(stage), cb * BK,
                                    im_w * p.conv_stride - p.conv_pad_w, im_h * p.conv_stride - p.conv_pad_h, im_n,
@@ -213,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      (uint16_t)b, (uint16_t)a);
                 }
               } else {
-                tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb * BK, mb * 128);
+                tma_load_2d(sA + stage * SM::kABytes, &tmA, full_bar(stage), kb2 * BK, mb * 128);
               }
               if (CTAS == 1 && AMODE == AMODE_STEM16)
                 tma_load_3d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), 0, nb * BLOCK_N, kb * 4);
@@ -221,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(sB + stage * SM::kBBytes, &tmB, full_bar(stage), kb * BK, nb * BLOCK_N);
             }
             __syncwarp();
-            if (AMODE == AMODE_IM2COL) {
+            if (AMODE == AMODE_IM2COL && kb >= p.kb_split) {
               if (++cb == p.conv_cblocks) {
                 cb = 0;
                 if (++tap_s == p.conv_kw) {

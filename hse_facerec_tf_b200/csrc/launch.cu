@@ -228,7 +228,7 @@ void launch_dw(const DwArgs& a, int prec, cudaStream_t s) {
 // CTAS = 2: CTA-pair tiles (256 rows); p.num_units / p.num_m_blocks then count pairs, and the grid is two CTAs per unit.
 template <typename T, int BLOCK_N, int EPI, int AMODE, int CTAS = 1>
 static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tR,
-                             const GemmParams& p, int device, cudaStream_t s) {
+                             const CUtensorMap& tA0, const GemmParams& p, int device, cudaStream_t s) {
   using SM = GemmSmem<BLOCK_N, EPI, CTAS>;
   auto kern = gemm_tc_kernel<T, BLOCK_N, EPI, AMODE, CTAS>;
   static std::atomic<bool> configured[64];
@@ -240,7 +240,7 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
   const int slots = device_sm_count(device) / CTAS;  // concurrently resident units
   int grid = (p.num_units < slots ? p.num_units : slots) * CTAS;
   if (grid < 1) return;
-  launch_pdl_cluster(kern, CTAS, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB, tD, tR, p);
+  launch_pdl_cluster(kern, CTAS, dim3(grid), dim3(384), (size_t)SM::kTotal, s, tA, tB, tD, tR, tA0, p);
   HFR_LAUNCH_CHECK("gemm_tc");
 }
 
@@ -298,9 +298,12 @@ void gemm_tile_choice(int64_t M, int N, int K, int conv_taps, int sms, int* ctas
 
 template <typename T, int AMODE>
 static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, GemmParams p, int64_t M, int N, int K,
-                              int prec, int device, cudaStream_t s) {
+                              int prec, int device, cudaStream_t s, const void* a0 = nullptr, int K0 = 0) {
+  // K is the TOTAL reduction length: K0 columns of the concatenated operand a0 (GemmParams::kb_split) + the main operand's
   CUtensorMap tD = make_tmap_2d(y, prec, (uint64_t)M, (uint64_t)N, 128);
   CUtensorMap tR = p.residual ? make_tmap_2d(p.residual, prec, (uint64_t)M, (uint64_t)N, 128) : tD;
+  CUtensorMap tA0 = a0 ? make_tmap_2d(a0, prec, (uint64_t)M, (uint64_t)K0, 128) : tA;
+  p.kb_split = a0 ? K0 / (128 / (int)elt_size(prec)) : 0;
   int ctas = 1, bn = 0;
   gemm_tile_choice(M, N, K, AMODE == AMODE_2D ? 0 : p.conv_kw * p.conv_kw, device_sm_count(device), &ctas, &bn);
   if (ctas == 2) {
@@ -310,8 +313,8 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
     p.num_n_blocks = N / pbn;
     p.n_blocks_per_unit = 1;
     p.num_units = p.num_m_blocks * p.num_n_blocks;
-    if (pbn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, p, device, s);
-    else launch_gemm_inst<T, 128, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, p, device, s);
+    if (pbn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, tA0, p, device, s);
+    else launch_gemm_inst<T, 128, EPI_STORE, AMODE, 2>(tA, tB, tD, tR, tA0, p, device, s);
     return;
   }
   // 1x1 layers are HBM / latency bound: 128-column tiles (twice the units, five 32 KB stages in flight instead of three
@@ -321,9 +324,9 @@ static void launch_gemm_store(const CUtensorMap& tA, const void* b, void* y, Gem
   p.num_n_blocks = (N + bn - 1) / bn;
   p.n_blocks_per_unit = 1;
   p.num_units = p.num_m_blocks * p.num_n_blocks;
-  if (bn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
-  else if (bn == 128) launch_gemm_inst<T, 128, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
-  else launch_gemm_inst<T, 64, EPI_STORE, AMODE>(tA, tB, tD, tR, p, device, s);
+  if (bn == 256) launch_gemm_inst<T, 256, EPI_STORE, AMODE>(tA, tB, tD, tR, tA0, p, device, s);
+  else if (bn == 128) launch_gemm_inst<T, 128, EPI_STORE, AMODE>(tA, tB, tD, tR, tA0, p, device, s);
+  else launch_gemm_inst<T, 64, EPI_STORE, AMODE>(tA, tB, tD, tR, tA0, p, device, s);
 }
 
 void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
@@ -338,13 +341,15 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s) {
   const int es = (int)elt_size(prec);
   if ((a.K * es) % 16 || (a.N * es) % 128) throw Error(-1, "gemm: K rows must be multiples of 16 bytes, N rows of 128 bytes");
   if (a.M >= (1ll << 31)) throw Error(-1, "gemm: M too large");
+  if (a.a0 && (a.K0 <= 0 || (a.K0 * es) % 128)) throw Error(-1, "gemm: the concatenated operand must be whole 128-byte k-blocks");
+  const int K0 = a.a0 ? a.K0 : 0;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = (int)a.M; p.N = a.N; p.K = a.K;
+  p.M = (int)a.M; p.N = a.N; p.K = K0 + a.K;
   p.bias = a.bias; p.residual = a.residual; p.act = a.act; p.round_tf32 = a.round_tf32;
   CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
-  if (prec == PREC_BF16) launch_gemm_store<__nv_bfloat16, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
-  else launch_gemm_store<float, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, a.K, prec, device, s);
+  if (prec == PREC_BF16) launch_gemm_store<__nv_bfloat16, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, p.K, prec, device, s, a.a0, K0);
+  else launch_gemm_store<float, AMODE_2D>(tA, a.b, a.y, p, a.M, a.N, p.K, prec, device, s, a.a0, K0);
 }
 
 // ---------------------------------------------------------------------------------------------- fused GEMM pair
@@ -366,7 +371,8 @@ bool gemm_pair_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int devi
   if (b.residual != nullptr) return false;
   if ((a.K * es) % 16 || a.N % 128) return false;     // whole 128-column tiles of Y; TMA row pitch
   if (b.N != 64 && b.N != 128 && b.N != 256) return false;   // the second accumulator: one tile of N2 TMEM columns
-  if (pair_num_kb(a.K, prec) > 4) return false;       // the unit's A rows stay resident in shared memory (<= 64 KB)
+  if (a.a0 && (a.K0 <= 0 || (a.K0 * es) % 128 || (a.K * es) % 128)) return false;
+  if (pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec) > 4) return false;   // the unit's A rows stay resident in shared memory (<= 64 KB)
   return true;
 }
 template <typename T, int N2, int NBUF, int PF>
@@ -381,26 +387,29 @@ static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec
   PairParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)a.M; p.num_m_blocks = (int)((a.M + 127) / 128);
-  p.N1 = a.N; p.K1 = a.K;
+  const int K0 = a.a0 ? a.K0 : 0;
+  p.N1 = a.N; p.K1 = K0 + a.K;
+  p.kb_split = K0 / (128 / (int)elt_size(prec));
   p.bias1 = a.bias; p.residual = a.residual; p.act1 = a.act; p.round1 = a.round_tf32;
   p.bias2 = b.bias; p.act2 = b.act; p.round2 = b.round_tf32;
-  const int num_kb = pair_num_kb(a.K, prec);
+  const int num_kb = pair_num_kb(p.K1, prec);
   p.na = num_kb <= 2 ? 2 : 1;
   p.stages = PairSmem::stages_for(num_kb, p.na, NBUF);
   const int grid = std::min(device_sm_count(device), p.num_m_blocks);
   CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
-  CUtensorMap tB1 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)a.K, 128);
+  CUtensorMap tA0 = a.a0 ? make_tmap_2d(a.a0, prec, (uint64_t)a.M, (uint64_t)K0, 128) : tA;
+  CUtensorMap tB1 = make_tmap_2d(a.b, prec, (uint64_t)a.N, (uint64_t)p.K1, 128);
   CUtensorMap tD1 = make_tmap_2d(a.y, prec, (uint64_t)a.M, (uint64_t)a.N, 128);
   CUtensorMap tR = a.residual ? make_tmap_2d(a.residual, prec, (uint64_t)a.M, (uint64_t)a.N, 128) : tD1;
   CUtensorMap tB2 = make_tmap_2d(b.b, prec, (uint64_t)b.N, (uint64_t)b.K, (uint32_t)std::min(N2, 128));
   CUtensorMap tD2 = make_tmap_2d(b.y, prec, (uint64_t)b.M, (uint64_t)b.N, 128);
-  launch_pdl(kern, dim3(grid), dim3(384), (size_t)PairSmem::total(num_kb, p.na, NBUF, p.stages), s, tA, tB1, tD1, tR, tB2, tD2, p);
+  launch_pdl(kern, dim3(grid), dim3(384), (size_t)PairSmem::total(num_kb, p.na, NBUF, p.stages), s, tA, tB1, tD1, tR, tB2, tD2, tA0, p);
   HFR_LAUNCH_CHECK("gemm_pair");
 }
 template <typename T, int N2>
 static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
   static const int bufs_env = getenv("HFR_SEAM_BUFS") ? atoi(getenv("HFR_SEAM_BUFS")) : 0;
-  const int num_kb = pair_num_kb(a.K, prec);
+  const int num_kb = pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec);
   int bufs = bufs_env ? bufs_env : 4;   // 4: residual chunks requested two ahead (stage 2: 192 -> 172 us per seam)
   // the weight ring keeps at least 4 slots: fewer staging buffers when the resident A rows are large
   while (bufs > 2 && PairSmem::stages_for(num_kb, num_kb <= 2 ? 2 : 1, bufs) < 4) --bufs;
@@ -454,14 +463,16 @@ void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s) {
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = (int)M; p.N = a.cout; p.K = a.kh * a.kw * a.cin;
+  if (a.a0 && (a.K0 <= 0 || a.K0 % bk)) throw Error(-1, "conv: the concatenated operand must be whole 128-byte k-blocks");
+  const int K0 = a.a0 ? a.K0 : 0;
+  p.M = (int)M; p.N = a.cout; p.K = K0 + a.kh * a.kw * a.cin;
   p.bias = a.bias; p.residual = a.residual; p.act = a.act; p.round_tf32 = a.round_tf32;
   p.conv_kw = a.kw; p.conv_cblocks = a.cin / bk; p.conv_wo = a.Wo; p.conv_ho = a.Ho;
   p.conv_stride = a.stride; p.conv_pad_w = a.pad_l; p.conv_pad_h = a.pad_t; p.conv_dil = a.dil;
   if (prec == PREC_BF16)
-    launch_gemm_store<__nv_bfloat16, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s);
+    launch_gemm_store<__nv_bfloat16, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s, a.a0, K0);
   else
-    launch_gemm_store<float, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s);
+    launch_gemm_store<float, AMODE_IM2COL>(tA, a.w, a.y, p, M, a.cout, p.K, prec, device, s, a.a0, K0);
 }
 
 // ---------------------------------------------------------------------------------------------- tensor-core stem
@@ -518,7 +529,7 @@ void launch_stem_tc(const StemTcArgs& a, int device, cudaStream_t s) {
   p.num_n_blocks = 1;
   p.n_blocks_per_unit = 1;
   p.num_units = p.num_m_blocks;
-  launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, tD, p, device, s);
+  launch_gemm_inst<__nv_bfloat16, 64, EPI_STORE, AMODE_STEM16>(tA, tB, tD, tD, tA, p, device, s);
 }
 
 // ---------------------------------------------------------------------------------------------- window conv
@@ -887,8 +898,8 @@ void launch_knn_gemm(const KnnGemmArgs& a, int prec, int device, cudaStream_t s)
   CUtensorMap tB = make_tmap_2d(a.g, prec, (uint64_t)a.n, (uint64_t)a.d, pair ? 128 : 256);
 #define HFR_KNN_LAUNCH(T, EPI)                                                                       \
   do {                                                                                               \
-    if (pair) launch_gemm_inst<T, 256, EPI, AMODE_2D, 2>(tA, tB, tA, tA, p, device, s);              \
-    else launch_gemm_inst<T, 256, EPI, AMODE_2D>(tA, tB, tA, tA, p, device, s);                      \
+    if (pair) launch_gemm_inst<T, 256, EPI, AMODE_2D, 2>(tA, tB, tA, tA, tA, p, device, s);              \
+    else launch_gemm_inst<T, 256, EPI, AMODE_2D>(tA, tB, tA, tA, tA, p, device, s);                      \
   } while (0)
   if (a.cand == 4) {
     if (prec == PREC_BF16) HFR_KNN_LAUNCH(__nv_bfloat16, EPI_KNN4); else HFR_KNN_LAUNCH(float, EPI_KNN4);

@@ -85,6 +85,9 @@ struct GemmArgs {
   int64_t M;
   int N, K;
   int act, round_tf32;
+  // K-concatenated operand: y = act([a0 | a] b^T + bias) with b = [N, K0 + K]; a0 is a plain [M, K0] matrix
+  const void* a0 = nullptr;
+  int K0 = 0;
 };
 void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s);
 // Two dependent 1x1 convolutions in one launch (gemm_pair.cuh): second.a must be first.y, same M, second.N in
@@ -104,6 +107,9 @@ struct ConvArgs {  // KxK convolution as implicit GEMM (NHWC), weights [cout][kh
   void* y;
   int B, H, W, cin, Ho, Wo, cout, kh, kw, stride, pad_t, pad_l, dil;
   int act, round_tf32;
+  // K-concatenated operand (see GemmArgs): a0 = plain [B*Ho*Wo, K0] matrix, w = [cout][K0 + kh*kw*cin]
+  const void* a0 = nullptr;
+  int K0 = 0;
 };
 void launch_conv(const ConvArgs& a, int prec, int device, cudaStream_t s);
 

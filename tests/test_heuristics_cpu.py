@@ -3,6 +3,7 @@ committed ncu launch list of the ResNet-50 benchmark step, and the k-NN gallery 
 import csv
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -30,6 +31,8 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
                 seen.add(r["ID"])
                 names.append(r["Kernel Name"])
     seq = []            # one entry per launch of an eager step, in order (see tools/traffic_from_launches.py)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from traffic_from_launches import kcat_absorbed
     sub_outs = {L["out"] for L in layers if L["kind"] == "subsample"}
     skip = False
     for i, L in enumerate(layers):
@@ -38,17 +41,20 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
         if skip:        # the 'reduce' half of a gemm_pair_kernel launch
             skip = False
             continue
+        if kcat_absorbed(layers, i, sub_outs):
+            continue    # 'increase' absorbed into the projection shortcut's GEMM (K-concatenation)
+        k0 = layers[i - 1]["cin"] if i > 0 and kcat_absorbed(layers, i - 1, sub_outs) else 0
         pair = None
         if L["kind"] == "pw" and i + 1 < len(layers) and L["in"] not in sub_outs:
             N = layers[i + 1]   # launch.cu: gemm_pair_eligible
             if (N["kind"] == "pw" and N["in"] == L["out"] and N.get("in2", -1) < 0 and L["cout"] % 128 == 0
-                    and N["cout"] in (64, 128, 256) and (L["cin"] + 63) // 64 <= 4):
+                    and N["cout"] in (64, 128, 256) and (k0 + L["cin"] + 63) // 64 <= 4):
                 pair, skip = N, True
-        seq += [(L, None), (L, None)] if L["kind"] == "stem" else [(L, pair)]
+        seq += [(L, None, 0), (L, None, 0)] if L["kind"] == "stem" else [(L, pair, k0)]
     names = names[:len(seq)]
-    assert len(names) == len(seq) == 48
+    assert len(names) == len(seq) == 44
     batch, checked, pairs = 256, 0, 0
-    for (L, pair), name in zip(seq, names):
+    for (L, pair, k0), name in zip(seq, names):
         if pair is not None:                                   # <T, N2, NBUF, PF>
             assert "gemm_pair_kernel" in name, (L["name"], name)
             assert int(name.split("<")[1].split(">")[0].replace(" ", "").split(",")[1]) == pair["cout"]
@@ -59,10 +65,10 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
         targs = name.split("<")[1].split(">")[0].replace(" ", "").split(",")      # <T, BLOCK_N, EPI, AMODE, CTAS>
         bn_seen, amode, ctas_seen = int(targs[1]), int(targs[3]), int(targs[4])
         taps = L["k"][0] * L["k"][1] if L["kind"] == "conv" else (1 if amode == 1 else 0)
-        M, N, K = batch * L["hw_out"][0] * L["hw_out"][1], L["cout"], L["cin"] * max(taps, 1)
+        M, N, K = batch * L["hw_out"][0] * L["hw_out"][1], L["cout"], k0 + L["cin"] * max(taps, 1)
         assert tile_choice(M, N, K, taps) == (ctas_seen, bn_seen), (L["name"], M, N, K, taps)
         checked += 1
-    assert pairs == 8 and checked == 49 - 16
+    assert pairs == 8 and checked == 49 - 16 - 4
 
 
 def test_tile_choice_policy_edges():

@@ -366,6 +366,38 @@ def test_tf32_tensor_core_stem_matches_the_cuda_core_stem(age_gender_pb, monkeyp
         assert cosine(got.cpu().numpy(), want.cpu().numpy()).min() > 0.99999
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_k_concatenated_projection_blocks_match_the_two_launch_form(precision, tmp_path, monkeypatch):
+    """First block of every ResNet stage: ReLU(increase(x_mid) + projection(x_in)) as ONE GEMM over the concatenated
+    reduction dimension (api.cu plan_kcat) against the plan's two-launch form (HFR_KCAT=0: 'increase' written in the
+    storage type, added as the residual).  Not bit-identical - the fused form keeps the sum in fp32 - so: four launches
+    fewer, every embedding within storage rounding of the two-launch one, and both equally close to the oracle
+    (the oracle comparisons of this file run with the default, fused, plan)."""
+    from hse_facerec_tf_b200.synth import write_resnet50_pb
+    pb = write_resnet50_pb(str(tmp_path / "vgg2_resnet.pb"), seed=11)
+    x = torch.from_numpy(np.ascontiguousarray(smooth_images(40, 224, 9))).cuda().contiguous()
+    monkeypatch.setenv("HFR_KCAT", "0")
+    m0 = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    (want,) = m0.forward(x, True, False)
+    n0 = hfr.launch_count()
+    m0.forward(x, True, False)
+    separate = hfr.launch_count() - n0
+    monkeypatch.setenv("HFR_KCAT", "1")
+    m1 = hfr.HfrModel(pb, "input:0", ["pool5_7x7_s1:0"], precision=precision)
+    n0 = hfr.launch_count()
+    (got,) = m1.forward(x, True, False)
+    fused = hfr.launch_count() - n0
+    assert fused == separate - 4, (fused, separate)
+    (again,) = m1.forward(x, True, False, graph=True)
+    torch.testing.assert_close(again, got, rtol=0, atol=0)
+    g, w = got.cpu().numpy(), want.cpu().numpy()
+    assert cosine(g, w).min() > (0.99999 if precision == "tf32" else 0.9995)
+    # with every activation kept the plan falls back to the two-launch form (the 'increase' tensor has to exist)
+    m1.keep_activations(True)
+    (kept,) = m1.forward(x, True, False)
+    torch.testing.assert_close(kept, want, rtol=0, atol=0)
+
+
 @pytest.mark.parametrize("batch", [3, 128])
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
 def test_fused_gemm_pairs_are_bit_identical_to_separate_launches(precision, batch, tmp_path, monkeypatch):

@@ -29,6 +29,21 @@ def kernel_class(name):
     return "other"
 
 
+def kcat_absorbed(layers, i, sub_outs):
+    """api.cu kcat_candidate (bf16): layer i is a linear 1x1 convolution whose only reader is the next 1x1 convolution's
+    residual input - the two run as one K-concatenated GEMM and layer i is not launched."""
+    if i + 1 >= len(layers):
+        return False
+    A, B = layers[i], layers[i + 1]
+    if A["kind"] != "pw" or B["kind"] != "pw" or A.get("act", "none") not in ("none", 0) or A.get("in2", -1) >= 0:
+        return False
+    if B.get("in2", -1) != A["out"] or B["in"] == A["out"] or A["cout"] != B["cout"] or A["hw_out"] != B["hw_out"]:
+        return False
+    if A["cin"] % 64 or B["cin"] % 64 or A["in"] in sub_outs:
+        return False
+    return not any(U is not B and (U["in"] == A["out"] or U.get("in2", -1) == A["out"]) for U in layers)
+
+
 def plan_classes(workload):
     """Class of every launch of one eager step, in launch order, from the compiled plan (host-only load): the same
     layer kinds bench.py books times under.  A bf16 stem is two launches (space-to-depth + window conv); a subsample
@@ -50,10 +65,13 @@ def plan_classes(workload):
         if fused_into_prev:          # second half of a gemm_pair_kernel launch (launch.cu: gemm_pair_eligible, bf16)
             fused_into_prev = False
             continue
+        if kcat_absorbed(layers, i, sub_outs):   # 'increase' absorbed by the projection shortcut's GEMM (api.cu: plan_kcat)
+            continue
         if L["kind"] == "pw" and i + 1 < len(layers) and L["in"] not in sub_outs:
             N = layers[i + 1]
+            k0 = layers[i - 1]["cin"] if i > 0 and kcat_absorbed(layers, i - 1, sub_outs) else 0
             fused_into_prev = (N["kind"] == "pw" and N["in"] == L["out"] and N.get("in2", -1) < 0 and L["cout"] % 128 == 0
-                               and N["cout"] in (64, 128, 256) and (L["cin"] + 63) // 64 <= 4)
+                               and N["cout"] in (64, 128, 256) and (k0 + L["cin"] + 63) // 64 <= 4)
         seq += ["stem", "stem"] if L["kind"] == "stem" else [L["kind"]]
     return seq
 

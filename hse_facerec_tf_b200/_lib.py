@@ -55,6 +55,7 @@ SIGNATURES = {
     "hfr_mtcnn_free": (None, [_vp]),
     "hfr_op_dwconv3x3": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "hfr_op_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "hfr_op_gemm_pair": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hfr_op_stem_conv": (_i, [_vp, _i, _vp, _vp, _vp] + [_i] * 15 + [_vp]),
     "hfr_op_stem_conv_tc": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "hfr_op_conv2d_window": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),

@@ -1350,6 +1350,28 @@ int hfr_op_gemm_bias_act(const void* a_, const void* b, const float* bias, const
   });
 }
 
+int hfr_op_gemm_pair(const void* a0, int k0, const void* a_, int k1, const void* w1, const float* bias1, const void* residual,
+                     void* y, int64_t m, int n1, int act1, const void* w2, const float* bias2, void* z, int n2, int act2,
+                     int dtype, int device, void* stream) {
+  return guarded([&] {
+    use_device(device);
+    if (!a_ || !w1 || !y) throw Error(HFR_ERR_INVALID, "null argument");
+    GemmArgs a;
+    a.a = a_; a.b = w1; a.bias = bias1; a.residual = residual; a.y = y; a.M = m; a.N = n1; a.K = k1; a.act = act1;
+    a.round_tf32 = (dtype == HFR_TF32 && z != nullptr);   // y feeds the second tf32 GEMM
+    a.a0 = a0; a.K0 = a0 ? k0 : 0;
+    if (!z) {
+      launch_gemm(a, dtype, device, (cudaStream_t)stream);
+      return;
+    }
+    GemmArgs b;
+    b.a = y; b.b = w2; b.bias = bias2; b.residual = nullptr; b.y = z; b.M = m; b.N = n2; b.K = n1; b.act = act2;
+    b.round_tf32 = 0;
+    if (!gemm_pair_eligible(a, b, dtype, device)) throw Error(HFR_ERR_UNSUPPORTED, "gemm pair: shapes not eligible");
+    launch_gemm_pair(a, b, dtype, device, (cudaStream_t)stream);
+  });
+}
+
 int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* bias, void* y, int batch, int h, int w_,
                      int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act,
                      int dtype, int device, void* stream) {

@@ -219,6 +219,13 @@ int hfr_op_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y
 /* y[M,N] = act(a[M,K] * b[N,K]^T + bias (+ residual[M,N])) */
 int hfr_op_gemm_bias_act(const void* a, const void* b, const float* bias, const void* residual, void* y, int64_t m,
                          int n, int k, int act, int dtype, int device, void* stream);
+/* The fused forms of the ResNet bottleneck seams (testing hooks of gemm_pair.cuh / GemmParams::kb_split):
+ *   y[M,N1] = act1([a0 | a] * w1^T + bias1 (+ residual)),   w1 = [N1, K0 + K1]  (a0 == NULL: no concatenated operand);
+ *   z == NULL:  that single K-concatenated GEMM;   otherwise also  z[M,N2] = act2(y * w2^T + bias2),  w2 = [N2, N1],
+ *   both GEMMs in ONE launch of gemm_pair_kernel (HFR_ERR_UNSUPPORTED when the shapes are not eligible). */
+int hfr_op_gemm_pair(const void* a0, int k0, const void* a, int k1, const void* w1, const float* bias1, const void* residual,
+                     void* y, int64_t m, int n1, int act1, const void* w2, const float* bias2, void* z, int n2, int act2,
+                     int dtype, int device, void* stream);
 int hfr_op_stem_conv(const void* x, int in_dtype, const float* w, const float* bias, void* y, int batch, int h, int w_,
                      int kh, int kw, int stride, int pad_t, int pad_l, int ho, int wo, int cout, int flags, int act,
                      int dtype, int device, void* stream);

@@ -71,6 +71,58 @@ def test_gemm_bias_act(prec, M, N, K):
         assert err <= tol * scale, f"M={M} N={N} K={K} prec={prec} act={act}: max err {err} (scale {scale})"
 
 
+# (M, K0, K1, N1, N2): K0 = columns of the concatenated operand (0: none), N2 = 0: single K-concatenated GEMM
+PAIR_CASES = [
+    (802816 // 16, 0, 64, 256, 64), (12544, 64, 64, 256, 64), (9408, 0, 128, 512, 128), (20000, 0, 256, 1024, 256),
+    (130, 0, 64, 128, 64), (128 * 149 + 5, 0, 128, 256, 128), (4000, 64, 128, 512, 256), (3000, 128, 128, 384, 64),
+    (5000, 64, 64, 256, 0), (7777, 128, 256, 512, 0), (20000, 256, 512, 1024, 0), (300, 512, 1024, 2048, 0),
+]
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("M,K0,K1,N1,N2", PAIR_CASES)
+def test_gemm_pair_and_k_concatenation(prec, M, K0, K1, N1, N2, monkeypatch):
+    """gemm_pair_kernel (two dependent 1x1 convolutions in one launch, the second fed from shared memory) and the
+    K-concatenated A operand, against fp64 matmuls of the same (exactly representable) operands: with and without the
+    shortcut, ragged M, fewer and more units than SMs, every (N2, staging-buffer) instantiation the launcher picks."""
+    monkeypatch.setenv("HFR_SEAM", "1")
+    es = 2 if prec == 2 else 4
+    if N2 and (K0 + K1) * es // 128 > 4:
+        pytest.skip("A rows of a unit exceed the resident buffer: not eligible in this precision (the launcher refuses)")
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * K1 + 5 * N1 + 7 * N2 + K0)
+    dt = TDT[prec]
+    rnd = (lambda t: tf32_round(t)) if prec == 1 else (lambda t: t)
+    a = rnd(torch.randn(M, K1, generator=g).to(DEV)).to(dt).contiguous()
+    a0 = rnd(torch.randn(M, K0, generator=g).to(DEV)).to(dt).contiguous() if K0 else None
+    w1 = rnd((torch.randn(N1, K0 + K1, generator=g) / (K0 + K1) ** 0.5).to(DEV)).to(dt).contiguous()
+    b1 = torch.randn(N1, generator=g).to(DEV)
+    res = rnd(torch.randn(M, N1, generator=g).to(DEV)).to(dt).contiguous()
+    w2 = rnd((torch.randn(max(N2, 1), N1, generator=g) / N1 ** 0.5).to(DEV)).to(dt).contiguous()
+    b2 = torch.randn(max(N2, 1), generator=g).to(DEV)
+    for use_res in (True, False):
+        y = torch.full((M, N1), float("nan"), dtype=dt, device=DEV)
+        z = torch.full((M, max(N2, 1)), float("nan"), dtype=dt, device=DEV)
+        check(lib.hfr_op_gemm_pair(_ptr(a0), K0, a.data_ptr(), K1, w1.data_ptr(), b1.data_ptr(), _ptr(res) if use_res else None,
+                                   y.data_ptr(), M, N1, 1, w2.data_ptr() if N2 else None, b2.data_ptr() if N2 else None,
+                                   z.data_ptr() if N2 else None, N2, 1, prec, 0, _stream()))
+        torch.cuda.synchronize()
+        acat = a.double() if a0 is None else torch.cat([a0.double(), a.double()], dim=1)
+        ref_y = acat @ w1.double().t() + b1.double()
+        if use_res:
+            ref_y = ref_y + res.double()
+        ref_y = torch.relu(ref_y)
+        tol = 2e-2 if prec == 2 else 2e-3
+        assert torch.isfinite(y.double()).all(), "kernel left unwritten / non-finite outputs"
+        err = (y.double() - ref_y).abs().max().item()
+        assert err <= tol * (ref_y.abs().max().item() + 1.0), f"Y: max err {err}"
+        if N2:
+            # the second GEMM consumes the ROUNDED y the kernel stored: compare against that, tightly
+            ref_z = torch.relu(y.double() @ w2.double().t() + b2.double())
+            assert torch.isfinite(z.double()).all()
+            errz = (z.double() - ref_z).abs().max().item()
+            assert errz <= tol * (ref_z.abs().max().item() + 1.0), f"Z: max err {errz}"
+
+
 # ------------------------------------------------------------------------------------------------ depthwise
 DW_CASES = [  # (B, H, W, C, stride)
     (2, 16, 16, 32, 1), (2, 16, 16, 64, 2), (3, 12, 12, 128, 1), (2, 14, 14, 512, 2), (2, 7, 7, 1024, 1),

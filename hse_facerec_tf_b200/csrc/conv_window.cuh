@@ -179,7 +179,10 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint64_t bd = b_desc0;
         uint32_t first = 0;
         if constexpr (TH > 0) {
-          // independent descriptor offsets, no loop-carried chain through the (slow) uniform datapath
+          // independent descriptor offsets, no loop-carried chain through the (slow) uniform datapath; 32-bit arithmetic
+          // on the descriptors' low words only (the offsets never reach the high word: start address + LBO fields)
+          const uint32_t a_lo = (uint32_t)a_row, a_hi = (uint32_t)(a_row >> 32);
+          const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
 #pragma unroll
           for (int ps = 0; ps < PASSES; ++ps)
 #pragma unroll
@@ -189,8 +192,8 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
                   const int i = ((ps * TH + r) * TW + s) * KS + j;
-                  umma<false>(d_tmem, a_row + (uint64_t)(r * a_row_step + s * a_col_step + j * a_k_step),
-                              bd + (uint64_t)(i * b_k_step), idesc, i != 0);
+                  umma_bf16_lohi(d_tmem, a_lo + (r * a_row_step + s * a_col_step + j * a_k_step), a_hi,
+                                 b_lo + (uint32_t)(i * b_k_step), b_hi, idesc, i != 0);
                 }
         } else
         for (int ps = 0; ps < PASSES; ++ps, a_row -= (uint64_t)p.taps_h * a_row_step)

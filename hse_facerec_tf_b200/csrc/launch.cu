@@ -375,6 +375,14 @@ bool gemm_pair_eligible(const GemmArgs& a, const GemmArgs& b, int prec, int devi
   if (pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec) > 4) return false;   // the unit's A rows stay resident in shared memory (<= 64 KB)
   return true;
 }
+// A buffers of a unit's resident rows: two (the next unit's rows arrive while this one computes) when they are small;
+// HFR_SEAM_NA=1: a single buffer whenever that buys the fourth staging buffer (A/B knob)
+static int pair_na(int num_kb, int nbuf) {
+  static const int na_env = getenv("HFR_SEAM_NA") ? atoi(getenv("HFR_SEAM_NA")) : 0;
+  if (num_kb > 2) return 1;
+  if (na_env == 1 && PairSmem::stages_for(num_kb, 2, nbuf) < 4) return 1;
+  return 2;
+}
 template <typename T, int N2, int NBUF, int PF>
 static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
   auto kern = gemm_pair_kernel<T, N2, NBUF, PF>;
@@ -393,7 +401,7 @@ static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec
   p.bias1 = a.bias; p.residual = a.residual; p.act1 = a.act; p.round1 = a.round_tf32;
   p.bias2 = b.bias; p.act2 = b.act; p.round2 = b.round_tf32;
   const int num_kb = pair_num_kb(p.K1, prec);
-  p.na = num_kb <= 2 ? 2 : 1;
+  p.na = pair_na(num_kb, NBUF);
   p.stages = PairSmem::stages_for(num_kb, p.na, NBUF);
   const int grid = std::min(device_sm_count(device), p.num_m_blocks);
   CUtensorMap tA = make_tmap_2d(a.a, prec, (uint64_t)a.M, (uint64_t)a.K, 128);
@@ -412,7 +420,7 @@ static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, 
   const int num_kb = pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec);
   int bufs = bufs_env ? bufs_env : 4;   // 4: residual chunks requested two ahead (stage 2: 192 -> 172 us per seam)
   // the weight ring keeps at least 4 slots: fewer staging buffers when the resident A rows are large
-  while (bufs > 2 && PairSmem::stages_for(num_kb, num_kb <= 2 ? 2 : 1, bufs) < 4) --bufs;
+  while (bufs > 2 && PairSmem::stages_for(num_kb, pair_na(num_kb, bufs), bufs) < 4) --bufs;
   if (bufs >= 4) launch_gemm_pair_inst<T, N2, 4, 2>(a, b, prec, device, s);
   else if (bufs == 3) launch_gemm_pair_inst<T, N2, 3, 1>(a, b, prec, device, s);
   else launch_gemm_pair_inst<T, N2, 2, 1>(a, b, prec, device, s);

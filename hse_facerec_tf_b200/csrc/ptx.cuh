@@ -202,6 +202,21 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
+// The same MMA (bf16, cta_group::1) with both descriptors given as 32-bit halves.  Only the low word of a descriptor
+// (start address, LBO) changes from one MMA to the next; with 64-bit descriptor arithmetic ptxas emitted a 64-bit uniform
+// add plus zeroed high words and register->uniform moves per operand (conv_window_kernel: ~270 instructions per 36-MMA
+// tile, issued in bursts - the tensor pipe idled half of the time behind the issue stream).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // CTA-pair MMA (M = 256 over two SMs): issued by the leader CTA only; both CTAs hold their 128 rows of A and their half
 // of B's N rows at the same shared-memory offsets, and each CTA's TMEM receives its own 128 rows x N columns.
 template <bool TF32>

@@ -245,13 +245,14 @@ static void launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
 }
 
 // CTA pairs halve the B (weight) bytes every SM pulls from L2 per k-block.  Measured per layer on ResNet-50 (B = 256):
-// the implicit-GEMM convolutions (long K, A re-read per tap from L2) gain 8-12 %, 1x1 layers with K >= 1024 gain 3-8 %,
+// the implicit-GEMM convolutions (long K, A re-read per tap from L2) gain 8-12 %, 1x1 layers with K >= 768 gain 3-18 %,
 // short-K 1x1 layers - HBM/epilogue-bound, where coupling two CTAs' epilogues only removes slack - lose 5-15 %.
 // Used when the output width splits into 256- or 128-column pair tiles and there is at least one full wave of pairs.
 static int pick_pair_block_n(int64_t M, int N, int K, int sms, bool im2col, bool multi_tap) {
   static const char* mode = getenv("HFR_PAIR");  // "0": never, "1": whenever the shape allows, unset: measured policy
   if (mode && mode[0] == '0') return 0;
-  if (!(mode && mode[0] == '1') && !multi_tap && K < 1024) return 0;
+  // (K = 768, the K-concatenated first block of stage 4: 87.6 us as single-CTA tiles, 71.6 us as pairs; K = 512: 39.5 vs 46)
+  if (!(mode && mode[0] == '1') && !multi_tap && K < 768) return 0;
   const bool need_even_m_blocks = im2col;  // im2col base pixels past the last image are not loaded
   const int64_t mb = (M + 127) / 128;
   if (need_even_m_blocks && (mb & 1)) return 0;

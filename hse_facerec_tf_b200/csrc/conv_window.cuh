@@ -245,18 +245,23 @@ conv_window_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t r[32];
+        const bool has_bias = (p.bias != nullptr && h * 32 < p.N);
+        float4 bb[8];     // bias loads ahead of the TMEM read: the two latencies overlap
+        if (has_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + h * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bb[q] = __ldg(b4 + q);
+        }
         tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + h * 32, r);
         tmem_ld_wait();
         float v[32];
-        if (p.bias != nullptr && h * 32 < p.N) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + h * 32);
+        if (has_bias) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bb = __ldg(b4 + q);
-            v[4 * q] = __uint_as_float(r[4 * q]) + bb.x;
-            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
-            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z;
-            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+            v[4 * q] = __uint_as_float(r[4 * q]) + bb[q].x;
+            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb[q].y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb[q].z;
+            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb[q].w;
           }
         } else {
 #pragma unroll

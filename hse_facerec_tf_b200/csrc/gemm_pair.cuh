@@ -378,18 +378,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int h = 0; h < CH_ELEMS / 32; ++h) {
           uint32_t r[32];
+          float4 bb[8];     // bias loads ahead of the TMEM read: the two latencies overlap
+          if (bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + h * 32);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) bb[qq] = __ldg(b4 + qq);
+          }
           tmem_ld_32x32(tmem_base + lane_addr + acc_col + c * CH_ELEMS + h * 32, r);
           tmem_ld_wait();
           float v[32];
           if (bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + h * 32);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
-              const float4 bb = __ldg(b4 + qq);
-              v[4 * qq] = __uint_as_float(r[4 * qq]) + bb.x;
-              v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb.y;
-              v[4 * qq + 2] = __uint_as_float(r[4 * qq + 2]) + bb.z;
-              v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb.w;
+              v[4 * qq] = __uint_as_float(r[4 * qq]) + bb[qq].x;
+              v[4 * qq + 1] = __uint_as_float(r[4 * qq + 1]) + bb[qq].y;
+              v[4 * qq + 2] = __uint_as_float(r[4 * qq + 2]) + bb[qq].z;
+              v[4 * qq + 3] = __uint_as_float(r[4 * qq + 3]) + bb[qq].w;
             }
           } else {
 #pragma unroll

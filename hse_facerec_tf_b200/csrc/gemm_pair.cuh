@@ -361,6 +361,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (isZ ? 0 : j * 128) + c * CH_ELEMS;
         const uint32_t b = ctr % NBUF, bi = g * NBUF + b;
         const uint32_t st_row = sEpi + bi * SLOT + row * 128;
+        // All TMEM loads of the chunk and the first bias vector go out first (asynchronous): their latency overlaps the
+        // leader's buffer hand-over and the wait for the residual chunk below.
+        constexpr int NH = CH_ELEMS / 32;
+        uint32_t racc[NH][32];
+        float4 bb[8];
+        auto load_bias = [&](int h) {
+          if (bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + h * 32);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) bb[qq] = __ldg(b4 + qq);
+          }
+        };
+        load_bias(0);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) tmem_ld_32x32(tmem_base + lane_addr + acc_col + c * CH_ELEMS + h * 32, racc[h]);
         if (leader) prefetch();   // the chunk PF ahead: frees its buffer (used NBUF - PF chunks ago), requests its residual
         uint4 rv[8];
         if (res) {
@@ -375,17 +390,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // (without a residual the buffer was freed by the leader PF chunks ago, ahead of a warpgroup barrier)
+        tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < CH_ELEMS / 32; ++h) {
-          uint32_t r[32];
-          float4 bb[8];     // bias loads ahead of the TMEM read: the two latencies overlap
-          if (bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + h * 32);
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) bb[qq] = __ldg(b4 + qq);
-          }
-          tmem_ld_32x32(tmem_base + lane_addr + acc_col + c * CH_ELEMS + h * 32, r);
-          tmem_ld_wait();
+        for (int h = 0; h < NH; ++h) {
+          uint32_t (&r)[32] = racc[h];
           float v[32];
           if (bias != nullptr) {
 #pragma unroll
@@ -399,6 +407,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]);
           }
+          if (h + 1 < NH) load_bias(h + 1);   // in flight during this half's residual add / pack / store
           if (res) {
             if constexpr (sizeof(T) == 4) {
 #pragma unroll

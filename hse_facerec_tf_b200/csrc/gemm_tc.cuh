@@ -365,6 +365,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n0 >= p.N) break;  // uniform across the CTA
           const uint32_t buf = chunk_ctr & 1;
           const uint32_t st_row = sEpi + (g * 2 + buf) * 16384 + row * 128;
+          // All TMEM loads of the chunk and the first bias vector are issued up front (asynchronous): their latency
+          // overlaps the wait for the residual tile / the staging buffer below instead of following it.
+          constexpr int NH = CH_ELEMS / 32;
+          uint32_t racc[NH][32];
+          float4 bb[8];
+          auto load_bias = [&](int h) -> bool {
+            const bool has = (p.bias != nullptr && n0 + h * 32 < p.N);
+            if (has) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + h * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) bb[q] = __ldg(b4 + q);
+            }
+            return has;
+          };
+          bool has_bias = load_bias(0);
+          // (plain 1x1 layers only: same-box A/B - those ran 2-5 % faster, the implicit-GEMM convolutions 2-3 % slower)
+          constexpr bool EARLY = (AMODE == AMODE_2D);
+          if constexpr (EARLY) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, racc[h]);
+          }
           uint4 rv[8];
           if (use_res) {
             if (leader) {
@@ -384,20 +405,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (leader) tma_store_wait_read<1>();
             named_bar_sync(bar_id, 128);
           }
+          if constexpr (EARLY) tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < CH_ELEMS / 32; ++h) {
-            uint32_t r[32];
-            // the bias loads are issued ahead of the TMEM read so that the two latencies overlap (they used to follow
-            // tcgen05.wait::ld: 11 % of the epilogue warps' stall samples sat on the first dependent add)
-            const bool has_bias = (p.bias != nullptr && n0 + h * 32 < p.N);
-            float4 bb[8];
-            if (has_bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + h * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) bb[q] = __ldg(b4 + q);
+          for (int h = 0; h < NH; ++h) {
+            uint32_t (&r)[32] = racc[h];
+            if constexpr (!EARLY) {   // one 32-column read at a time, right before its use
+              tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, r);
+              tmem_ld_wait();
             }
-            tmem_ld_32x32(tmem_base + lane_addr + as * BLOCK_N + c * CH_ELEMS + h * 32, r);
-            tmem_ld_wait();
             float v[32];
             if (has_bias) {
 #pragma unroll
@@ -411,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             }
+            if (h + 1 < NH) has_bias = load_bias(h + 1);   // in flight during this half's residual add / pack / store
             if (use_res) {
               if constexpr (sizeof(T) == 4) {
 #pragma unroll

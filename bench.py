@@ -227,7 +227,7 @@ def bench_network(workload, precision, args, rank, world, dev):
         # untimed pre-roll of the same steps so that nvidia-smi (100 ms period) sees the GPU under this load even when
         # the K timed steps last only a few milliseconds; the sampler keeps running through the timed region
         t_pre = time.perf_counter()
-        while time.perf_counter() - t_pre < 0.5:
+        while time.perf_counter() - t_pre < 1.0:
             for i in range(8):
                 step(i)
             stream.synchronize()
@@ -377,6 +377,7 @@ def bench_network(workload, precision, args, rank, world, dev):
     rec = dict(metric=metric, value=round(total / (ms * 1e-3), 1), unit=unit, n_gpus=world, steps=steps, warmup=warmup,
                ms_per_step=round(ms / steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype=precision, data="synthetic", config=workload_config(workload, world, batch), cuda_graph=not args.no_graph)
+    rec["per_gpu_value"] = round(rec["value"] / world, 1)     # `value` is the whole job; ratios against ONE host belong to this
     if e2e_s is not None:
         rec["e2e"] = dict(value=round(total / e2e_s, 1), unit=unit, h2d_bytes_per_step=in_bytes,
                           d2h_bytes_per_step=sum(out_dims) * 4 * batch,
@@ -442,7 +443,7 @@ def bench_knn(precision, args, rank, world, dev):
         sampler = ClockSampler(dev)
         sampler.start()
         t_pre = time.perf_counter()
-        while time.perf_counter() - t_pre < 0.5:     # untimed pre-roll: the clock sampler sees the GPU under this load
+        while time.perf_counter() - t_pre < 1.0:     # untimed pre-roll: the clock sampler sees the GPU under this load
             clf.kneighbors(qd, return_distance=False)
         if world > 1:
             dist.barrier()
@@ -495,6 +496,7 @@ def bench_knn(precision, args, rank, world, dev):
     rec = dict(metric=metric, value=round(nq * steps / (ms * 1e-3), 1), unit=unit, n_gpus=world, steps=steps,
                warmup=warmup, ms_per_step=round(per_step_ms, 3), higher_is_better=True, scaling="strong",
                vs_baseline=None, dtype=precision, data="synthetic", config=cfg)
+    rec["per_gpu_value"] = round(rec["value"] / world, 1)
     if e2e_s is not None:
         rec["e2e"] = dict(value=round(nq * steps / e2e_s, 1), unit=unit, h2d_bytes_per_step=(b - a) * d * 4,
                           d2h_bytes_per_step=nq * 8,

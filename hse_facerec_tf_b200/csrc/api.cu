@@ -189,6 +189,7 @@ struct hfr_model {
   std::vector<LayerDev> dev;
   // activation arena: per-image byte offsets of every value (multiplied by the batch at run time)
   std::vector<size_t> val_off, val_bytes;
+  std::vector<int> val_release;   // layer after which a value's arena slot is free again (-1: never / not materialised)
   size_t per_image_bytes = 0;
   bool keep_all = false;
   bool stem_force_direct = getenv("HFR_STEM_DIRECT") != nullptr;  // debugging: CUDA-core stem in every mode
@@ -321,8 +322,12 @@ struct hfr_model {
     kcat_skip.assign(n, 0);
     const char* e = getenv("HFR_KCAT");
     if (keep_all || (e && atoi(e) == 0)) return;
+    // (a host-only handle has no device weights; HFR_PLAN_ASSUME_KCAT=1 lets it plan as the device handle would, so that
+    // the arena layout of the fused plan can be checked without a GPU: tests/test_arena_cpu.py)
+    const bool assume = device < 0 && getenv("HFR_PLAN_ASSUME_KCAT") != nullptr;
     for (size_t i = 0; i + 1 < n; ++i) {
-      if (!kcat_candidate(i) || gather_of[i] >= 0 || dev.size() != n || dev[i + 1].w_cat == nullptr) continue;
+      if (!kcat_candidate(i) || gather_of[i] >= 0) continue;
+      if (!assume && (dev.size() != n || dev[i + 1].w_cat == nullptr)) continue;
       kcat_of[i + 1] = (int)i;
       kcat_skip[i] = 1;
     }
@@ -407,26 +412,38 @@ struct hfr_model {
         }
       }
     };
+    // Two 1x1 convolutions that may run as ONE gemm_pair_kernel launch (decided per call: gemm_pair_eligible): the second
+    // layer's output is written while other CTAs still read the first layer's inputs, so those inputs must outlive the
+    // second layer's allocation - otherwise first-fit could hand the second output the slot the first layer's residual
+    // (or input) has just left.  Every input of layer li stays live through layer li + 1.
+    for (size_t li = 0; li + 1 < plan.layers.size(); ++li) {
+      const Layer& A = plan.layers[li];
+      const Layer& B = plan.layers[li + 1];
+      if (precision == HFR_FP32 || A.kind != L_PW || B.kind != L_PW || B.in != A.out || B.in2 >= 0) continue;
+      if (gather_of[li] >= 0 || gather_of[li + 1] >= 0 || kcat_skip[li]) continue;
+      int ins[3] = {A.in, kcat_of[li] >= 0 ? -1 : A.in2, kcat_of[li] >= 0 ? plan.layers[(size_t)kcat_of[li]].in : -1};
+      for (int v : ins)
+        if (v > 0 && last_use[(size_t)v] < (int)li + 1) last_use[(size_t)v] = (int)li + 1;
+    }
+    val_release.assign((size_t)nv, -1);
+    std::vector<char> live((size_t)nv, 0);
     for (int li = 0; li < (int)plan.layers.size(); ++li) {
       const Layer& L = plan.layers[(size_t)li];
-      if (skip_layer[(size_t)li] || kcat_skip[(size_t)li]) {  // never materialised; its input may end its life here unless a later layer reads it in its place
-        if (L.in > 0 && last_use[(size_t)L.in] == li) release(val_off[(size_t)L.in], val_bytes[(size_t)L.in]);
-        continue;
+      if (!(skip_layer[(size_t)li] || kcat_skip[(size_t)li])) {   // (those layers' outputs are never materialised)
+        val_bytes[(size_t)L.out] = value_image_bytes(L.out);
+        val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
+        live[(size_t)L.out] = 1;
       }
-      val_bytes[(size_t)L.out] = value_image_bytes(L.out);
-      val_off[(size_t)L.out] = alloc(val_bytes[(size_t)L.out]);
       if (keep_all) continue;
-      int ins[3] = {L.in, L.in2, -1};
-      if (gather_of[(size_t)li] >= 0) ins[0] = plan.layers[(size_t)gather_of[(size_t)li]].in;
-      if (kcat_of[(size_t)li] >= 0) {   // no residual tensor exists; the absorbed layer's input is read instead
-        ins[1] = -1;
-        ins[2] = plan.layers[(size_t)kcat_of[(size_t)li]].in;
+      // every value whose last reader is this layer leaves the arena now (after this layer's output was placed)
+      for (int v = 1; v < nv; ++v) {
+        if (!live[(size_t)v]) continue;
+        if (last_use[(size_t)v] == li || (v == L.out && last_use[(size_t)v] < 0)) {
+          release(val_off[(size_t)v], val_bytes[(size_t)v]);
+          live[(size_t)v] = 0;
+          val_release[(size_t)v] = li;
+        }
       }
-      for (int v : ins) {
-        if (v <= 0) continue;  // value 0 is the caller's input
-        if (last_use[(size_t)v] == li) release(val_off[(size_t)v], val_bytes[(size_t)v]);
-      }
-      if (last_use[(size_t)L.out] < 0) release(val_off[(size_t)L.out], val_bytes[(size_t)L.out]);
     }
     per_image_bytes = top;
   }
@@ -864,8 +881,19 @@ int hfr_model_info(const hfr_model* m, int* in_h, int* in_w, int* in_c, int* n_o
 int64_t hfr_model_plan_json(const hfr_model* m, char* buf, int64_t buf_len) {
   if (!m) return HFR_ERR_INVALID;
   std::string js = m->plan.to_json();
+  // arena layout per value: [value id, producer layer, byte offset per image, bytes per image, layer after which it is free]
+  std::string arena = ",\"arena\":[";
+  bool first = true;
+  for (size_t v = 1; v < m->plan.values.size() && v < m->val_bytes.size(); ++v) {
+    if (m->val_bytes[v] == 0) continue;
+    arena += std::string(first ? "" : ",") + "[" + std::to_string(v) + "," + std::to_string(m->plan.values[v].producer) + "," +
+             std::to_string(m->val_off[v]) + "," + std::to_string(m->val_bytes[v]) + "," +
+             std::to_string(v < m->val_release.size() ? m->val_release[v] : -1) + "]";
+    first = false;
+  }
+  arena += "]";
   js.insert(js.size() - 1, ",\"arena_bytes_per_image\":" + std::to_string(m->per_image_bytes) +
-                               ",\"precision\":" + std::to_string(m->precision));
+                               ",\"precision\":" + std::to_string(m->precision) + arena);
   if (buf && buf_len > (int64_t)js.size()) memcpy(buf, js.c_str(), js.size() + 1);
   return (int64_t)js.size() + 1;
 }

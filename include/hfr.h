@@ -68,7 +68,9 @@ int64_t hfr_launch_count(void);
 int hfr_model_load(const char* path, const char* input_name, const char* output_names_csv, const char* phase_name,
                    float phase_value, int input_hw, int device, int precision, hfr_model** out);
 int hfr_model_info(const hfr_model* m, int* in_h, int* in_w, int* in_c, int* n_outputs, int* out_dims /*[n_outputs]*/);
-/* Fused layer plan as JSON (for tests / inspection).  Returns the length needed (incl. NUL) if buf is too small. */
+/* Fused layer plan as JSON (for tests / inspection): layers, outputs, and "arena" = the activation arena's layout, one
+ * [value id, producer layer, byte offset per image, bytes per image, layer after which the slot is free (-1: never)]
+ * per materialised value.  Returns the length needed (incl. NUL) if buf is too small. */
 int64_t hfr_model_plan_json(const hfr_model* m, char* buf, int64_t buf_len);
 
 /* Folded fp32 weights / bias of plan layer `layer` as the compiler produced them (layouts: see "w" in the plan JSON

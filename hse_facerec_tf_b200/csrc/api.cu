@@ -425,6 +425,13 @@ struct hfr_model {
       for (int v : ins)
         if (v > 0 && last_use[(size_t)v] < (int)li + 1) last_use[(size_t)v] = (int)li + 1;
     }
+    // The fused dense tail (dense_heads_kernel: hidden layer + every head in one launch) writes the heads' outputs while
+    // other CTAs still read the pooled vector: it stays live through the last layer of the group.
+    if (head_first >= 0 && head_count > 1) {
+      const int v = plan.layers[(size_t)head_first].in;
+      const int last = head_first + head_count - 1;
+      if (v > 0 && last_use[(size_t)v] < last) last_use[(size_t)v] = last;
+    }
     val_release.assign((size_t)nv, -1);
     std::vector<char> live((size_t)nv, 0);
     for (int li = 0; li < (int)plan.layers.size(); ++li) {

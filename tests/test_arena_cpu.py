@@ -78,3 +78,20 @@ def test_arena_slots_are_reused_only_by_dead_values(workload, precision, assume_
                 assert not overlaps(z, arena[v]), f"seam {A['name']} -> {B['name']}: output {z} overlaps input {arena[v]}"
     if workload == "resnet50":
         assert seams >= 8
+
+
+def test_fused_dense_tail_keeps_the_pooled_vector_alive():
+    """dense_heads_kernel runs the hidden Dense layer and both heads in one launch: with only the heads requested (the
+    pooled embedding is then an ordinary intermediate) its slot must not be handed to a head output."""
+    spec = bench.model_spec("agegender224")
+    m = hfr.HfrModel(spec["path"], spec["input"], ["age_pred/Softmax:0", "gender_pred/Sigmoid:0"], input_hw=0, device=None,
+                     precision="bf16")
+    plan = m.plan()
+    layers = plan["layers"]
+    arena = {a[0]: a for a in plan["arena"]}
+    fc = [i for i, L in enumerate(layers) if L["kind"] == "fc"]
+    assert len(fc) == 3 and fc == list(range(fc[0], fc[0] + 3))
+    pooled = arena[layers[fc[0]]["in"]]
+    assert pooled[4] == fc[-1], pooled                      # released after the LAST layer of the fused group
+    for i in fc:
+        assert not overlaps(arena[layers[i]["out"]], pooled)

@@ -16,8 +16,9 @@
 //                 K-blocks of the PREVIOUS Y tile (N2 rows x 128 bytes each: two per slot for N2 = 64, two slots = two
 //                 128-column halves for N2 = 256)
 //   warp 3        TMA producer of the unit's A rows: all K1/BK k-blocks of a 128-row block stay RESIDENT for the unit's
-//                 N1/128 Y tiles (re-streaming them per tile made stages 3-4 L2->SM-bound: 8 x 64 KB per unit in stage
-//                 4); double-buffered across units when K1 <= 2 k-blocks
+//                 N1/128 Y tiles (the first version re-streamed them with W1 for every tile, 8 x 64 KB per unit in
+//                 stage 4; resident rows + 16 KB slots: stage-2 seams -10 %, stage 4 unchanged); double-buffered
+//                 across units when K1 <= 2 k-blocks
 //   warp 1        MMA issuer:  GEMM1(tile q) into accumulator stage q & 1, then GEMM2 of tile q-1 (its chunks are being
 //                 staged by an epilogue warpgroup while GEMM1(q) runs), commit -> sfree[buffer], last chunk -> zfull
 //   warp 2        TMEM allocator (512 columns: 2 x 128 for Y tiles, N2 <= 256 for Z)
@@ -28,6 +29,9 @@
 //   [leader] previous TMA store has finished reading it  &&  previous GEMM2 that read it has retired (sfree)
 //   -> residual chunk lands in it by TMA (rfull), PF chunks ahead  -> epilogue adds accumulator, writes the result in
 //   place -> fence.proxy.async + warpgroup barrier -> TMA store of the chunk  +  arrive(sfull) -> GEMM2 reads it.
+//
+// Memory: Z is written while other CTAs still read A, A0 and R, so Z (like Y) must not share memory with any of them -
+// the arena planner keeps the first layer's inputs live through the second layer (api.cu plan_arena, seam rule).
 //
 // Reference semantics being replaced: the `convN_M_1x1_increase` + `Add` + `Relu` and `convN_(M+1)_1x1_reduce` + `Relu`
 // nodes of the frozen ResNet-50 graph, evaluated by sess.run (facerec_test.py:114-122).

@@ -34,6 +34,7 @@ SIGNATURES = {
     "hfr_resize_pil_u8": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "hfr_debug_gemm_tile_choice": (_i, [_i64, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "hfr_debug_knn_plan": (_i, [_i64, _i64, C.POINTER(_i), C.POINTER(_i)]),
+    "hfr_debug_gemm_pair_config": (_i, [_i64, _i, _i, _i, _i, _i, _i] + [C.POINTER(_i)] * 6),
     "hfr_pairwise_dist": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _i, _vp]),
     "hfr_age_gender_post": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hfr_l2_normalize": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

@@ -1134,6 +1134,27 @@ int hfr_debug_gemm_tile_choice(int64_t m, int n, int k, int conv_taps, int sms, 
   });
 }
 
+int hfr_debug_gemm_pair_config(int64_t m, int k0, int k1, int n1, int n2, int has_residual, int precision, int* eligible,
+                               int* nbuf, int* pf, int* na, int* stages, int* smem_bytes) {
+  return guarded([&] {
+    if (!eligible || !nbuf || !pf || !na || !stages || !smem_bytes || m <= 0 || k1 <= 0 || n1 <= 0 || n2 <= 0 || k0 < 0)
+      throw Error(HFR_ERR_INVALID, "bad argument");
+    // the launcher's own predicate on stand-in operands (only their identity matters: second.a == first.y)
+    static char x0, xa, xy, xz, xr;
+    GemmArgs a, b;
+    a.a = &xa; a.b = &xa; a.bias = nullptr; a.residual = has_residual ? &xr : nullptr; a.y = &xy; a.M = m; a.N = n1; a.K = k1;
+    a.act = 1; a.round_tf32 = 0; a.a0 = k0 ? &x0 : nullptr; a.K0 = k0;
+    b.a = &xy; b.b = &xa; b.bias = nullptr; b.residual = nullptr; b.y = &xz; b.M = m; b.N = n2; b.K = n1; b.act = 1;
+    b.round_tf32 = 0;
+    *eligible = gemm_pair_eligible(a, b, precision, 0) ? 1 : 0;
+    *nbuf = *pf = *na = *stages = *smem_bytes = 0;
+    if (*eligible) {
+      const int bk = precision == HFR_BF16 ? 64 : 32;
+      gemm_pair_config((k0 + k1 + bk - 1) / bk, nbuf, pf, na, stages, smem_bytes);
+    }
+  });
+}
+
 int hfr_debug_knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit) {
   return guarded([&] {
     if (!splits || !n_blocks_per_unit || nq <= 0 || n <= 0) throw Error(HFR_ERR_INVALID, "bad argument");

@@ -415,15 +415,25 @@ static void launch_gemm_pair_inst(const GemmArgs& a, const GemmArgs& b, int prec
   launch_pdl(kern, dim3(grid), dim3(384), (size_t)PairSmem::total(num_kb, p.na, NBUF, p.stages), s, tA, tB1, tD1, tR, tB2, tD2, tA0, p);
   HFR_LAUNCH_CHECK("gemm_pair");
 }
-template <typename T, int N2>
-static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+// Staging buffers per epilogue warpgroup, residual prefetch distance, A buffers, ring slots and dynamic shared memory of
+// the fused kernel for a first GEMM of `num_kb` 128-byte k-blocks (host logic, also behind hfr_debug_gemm_pair_config).
+void gemm_pair_config(int num_kb, int* nbuf, int* pf, int* na, int* stages, int* smem_bytes) {
   static const int bufs_env = getenv("HFR_SEAM_BUFS") ? atoi(getenv("HFR_SEAM_BUFS")) : 0;
-  const int num_kb = pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec);
   int bufs = bufs_env ? bufs_env : 4;   // 4: residual chunks requested two ahead (stage 2: 192 -> 172 us per seam)
   // the weight ring keeps at least 4 slots: fewer staging buffers when the resident A rows are large
   while (bufs > 2 && PairSmem::stages_for(num_kb, pair_na(num_kb, bufs), bufs) < 4) --bufs;
-  if (bufs >= 4) launch_gemm_pair_inst<T, N2, 4, 2>(a, b, prec, device, s);
-  else if (bufs == 3) launch_gemm_pair_inst<T, N2, 3, 1>(a, b, prec, device, s);
+  *nbuf = bufs >= 4 ? 4 : (bufs == 3 ? 3 : 2);
+  *pf = *nbuf == 4 ? 2 : 1;
+  *na = pair_na(num_kb, *nbuf);
+  *stages = PairSmem::stages_for(num_kb, *na, *nbuf);
+  *smem_bytes = PairSmem::total(num_kb, *na, *nbuf, *stages);
+}
+template <typename T, int N2>
+static void launch_gemm_pair_n2(const GemmArgs& a, const GemmArgs& b, int prec, int device, cudaStream_t s) {
+  int nbuf, pf, na, stages, smem;
+  gemm_pair_config(pair_num_kb((a.a0 ? a.K0 : 0) + a.K, prec), &nbuf, &pf, &na, &stages, &smem);
+  if (nbuf == 4) launch_gemm_pair_inst<T, N2, 4, 2>(a, b, prec, device, s);
+  else if (nbuf == 3) launch_gemm_pair_inst<T, N2, 3, 1>(a, b, prec, device, s);
   else launch_gemm_pair_inst<T, N2, 2, 1>(a, b, prec, device, s);
 }
 template <typename T>

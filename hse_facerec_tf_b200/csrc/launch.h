@@ -94,6 +94,7 @@ void launch_gemm(const GemmArgs& a, int prec, int device, cudaStream_t s);
 // {64, 128, 256}, no residual on the second; the second GEMM's A operand never leaves shared memory.
 bool gemm_pair_eligible(const GemmArgs& first, const GemmArgs& second, int prec, int device);
 void launch_gemm_pair(const GemmArgs& first, const GemmArgs& second, int prec, int device, cudaStream_t s);
+void gemm_pair_config(int num_kb, int* nbuf, int* pf, int* na, int* stages, int* smem_bytes);
 // fp32-accurate y[M, N] = act(a[M,K] b[N,K]^T + bias) on the tensor cores (3xTF32, kernels.cuh); ldy >= N is y's row
 // pitch in floats.  Needs K % 4 == 0; scratch comes from the stream-ordered allocator.
 void launch_gemm_x3(const float* a, const float* b, const float* bias, float* y, int64_t M, int N, int K, int64_t ldy, int act,

@@ -117,6 +117,11 @@ int hfr_crop_resize_u8(const uint8_t* frames, int n_frames, int frame_h, int fra
  * of an implicit-GEMM convolution, 0 for a plain GEMM), and the gallery split of the k-NN kernel. */
 int hfr_debug_gemm_tile_choice(int64_t m, int n, int k, int conv_taps, int sms, int* ctas, int* block_n);
 int hfr_debug_knn_plan(int64_t nq, int64_t n, int* splits, int* n_blocks_per_unit);
+/* ... and whether two dependent 1x1 convolutions  y = act([a0 | a] w1^T (+ r)) [m, n1],  z = act(y w2^T) [m, n2]  run as
+ * one gemm_pair_kernel launch (k0 = columns of the concatenated operand, 0: none), and with which configuration: staging
+ * buffers per epilogue warpgroup, residual prefetch distance, A buffers, 16 KB ring slots, dynamic shared memory. */
+int hfr_debug_gemm_pair_config(int64_t m, int k0, int k1, int n1, int n2, int has_residual, int precision, int* eligible,
+                               int* nbuf, int* pf, int* na, int* stages, int* smem_bytes);
 /* Distance matrix for the clustering scripts: out[i,j] = ||x_i - y_j||_2 (float32 [n,m], device), the per-pair
  * expression of process_photos.py:46-48 and sklearn.metrics.pairwise_distances(X_norm) of facial_clustering_test.py:396;
  * y == NULL: y = x (m == n, exact zeros on the diagonal).  With year/born (device float32 [n] / [m], all four or none):

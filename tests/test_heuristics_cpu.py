@@ -20,6 +20,12 @@ def tile_choice(m, n, k, taps, sms=148):
     return ctas.value, bn.value
 
 
+def pair_config(m, k0, k1, n1, n2, has_res=1, prec=2):
+    vals = [C.c_int() for _ in range(6)]
+    check(lib.hfr_debug_gemm_pair_config(m, k0, k1, n1, n2, has_res, prec, *[C.byref(v) for v in vals]))
+    return [v.value for v in vals]          # eligible, nbuf, pf, na, stages, smem bytes
+
+
 def test_tile_choice_reproduces_the_profiled_resnet50_step():
     spec = bench.model_spec("resnet50")
     m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
@@ -57,7 +63,11 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
     for (L, pair, k0), name in zip(seq, names):
         if pair is not None:                                   # <T, N2, NBUF, PF>
             assert "gemm_pair_kernel" in name, (L["name"], name)
-            assert int(name.split("<")[1].split(">")[0].replace(" ", "").split(",")[1]) == pair["cout"]
+            targs = name.split("<")[1].split(">")[0].replace(" ", "").split(",")      # <T, N2, NBUF, PF>
+            assert int(targs[1]) == pair["cout"]
+            M = batch * L["hw_out"][0] * L["hw_out"][1]
+            e, nbuf, pf, na, stages, smem = pair_config(M, k0, L["cin"], L["cout"], pair["cout"], has_res=int(k0 == 0))
+            assert e == 1 and (nbuf, pf) == (int(targs[2]), int(targs[3])), (L["name"], name, nbuf, pf)
             pairs += 1
             continue
         if "gemm_tc_kernel" not in name:
@@ -69,6 +79,31 @@ def test_tile_choice_reproduces_the_profiled_resnet50_step():
         assert tile_choice(M, N, K, taps) == (ctas_seen, bn_seen), (L["name"], M, N, K, taps)
         checked += 1
     assert pairs == 8 and checked == 49 - 16 - 4
+
+
+def test_gemm_pair_eligibility_and_configuration():
+    """The launcher's own predicate and configuration choice for the fused 'increase' + 'reduce' launch (launch.cu:
+    gemm_pair_eligible / gemm_pair_config), on ResNet-50's seams at batch 256 and on the shapes that must be refused."""
+    M = 256 * 56 * 56
+    # stage 2 (K1 = 64): two A buffers, four staging buffers with the residual two chunks ahead, >= 4 ring slots
+    assert pair_config(M, 0, 64, 256, 64) == [1, 4, 2, 2, 4, 1024 + (2 + 4 + 8) * 16384 + 512]
+    # ... and its K-concatenated first block (64 + 64 columns, no residual tensor): three staging buffers
+    e, nbuf, pf, na, stages, smem = pair_config(M, 64, 64, 256, 64, has_res=0)
+    assert (e, nbuf, pf, na) == (1, 3, 1, 2) and stages >= 4
+    # stage 3 (K1 = 128) and stage 4 (K1 = 256: one resident A buffer of 64 KB)
+    assert pair_config(M // 4, 0, 128, 512, 128)[:4] == [1, 3, 1, 2]
+    assert pair_config(M // 16, 0, 256, 1024, 256)[:4] == [1, 3, 1, 1]
+    for args in ((M, 0, 64, 256, 64), (M, 64, 64, 256, 64), (M // 4, 0, 128, 512, 128), (M // 16, 0, 256, 1024, 256)):
+        e, nbuf, pf, na, stages, smem = pair_config(*args)
+        assert e == 1 and 4 <= stages <= 8 and smem <= 227 * 1024 and 1 <= pf < nbuf
+    # refused: stage 5 (the second accumulator would need 512 TMEM columns), A rows beyond the resident buffer (K1 = 512;
+    # tf32 stage 4: 256 floats = 8 k-blocks), a first GEMM whose width is not whole 128-column tiles, fp32 mode
+    assert pair_config(M // 64, 0, 512, 2048, 512)[0] == 0
+    assert pair_config(M // 16, 0, 512, 1024, 256)[0] == 0
+    assert pair_config(M // 16, 0, 256, 1024, 256, prec=1)[0] == 0
+    assert pair_config(M // 4, 0, 128, 512, 128, prec=1)[:2] == [1, 3]
+    assert pair_config(M, 0, 64, 192, 64)[0] == 0
+    assert pair_config(M, 0, 64, 256, 64, prec=0)[0] == 0
 
 
 def test_tile_choice_policy_edges():

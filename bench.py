@@ -180,8 +180,44 @@ def plan_work(plan, es):
             in_b, out_b = L["cin"] * 4, L["cout"] * 4
         res_b = ho * wo * L["cout"] * es if L["in2"] >= 0 else 0
         rows.append(dict(kind=kind, name=L["name"], flops=flops, bytes=float(in_b + res_b + out_b), out_bytes=float(out_b),
-                         in_bytes=float(in_b), res_bytes=float(res_b), out=L["out"], in2=L["in2"]))
+                         in_bytes=float(in_b), res_bytes=float(res_b), out=L["out"], in2=L["in2"], **{"in": L["in"]}))
     return rows
+
+
+def merge_fused_launches(work, per_step):
+    """Per-layer work rows (plan_work) + per-layer times (-1: nothing was launched for that layer) -> one (row, time) per
+    LAUNCH, with the algorithmic work the launch really has:
+      * a bypassed gather (strided 1x1 consumers fetch through an im2col map) disappears;
+      * an 'increase' 1x1 convolution absorbed by the projection shortcut it is the residual of (api.cu: plan_kcat) adds its
+        flops and its INPUT bytes to that GEMM, whose residual tensor no longer exists;
+      * two 1x1 convolutions in one gemm_pair_kernel launch: both layers' flops, the first layer's bytes plus the second
+        layer's OUTPUT only (its input never leaves the SM)."""
+    merged = []
+    i = 0
+    absorbed = None
+    while i < len(work):
+        w, t = dict(work[i]), per_step[i]
+        if t < 0:
+            if (w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] >= 0
+                    and work[i + 1]["in2"] == w["out"]):
+                absorbed = w
+            i += 1
+            continue
+        if absorbed is not None:
+            w["name"] = absorbed["name"] + " (+) " + w["name"]
+            w["flops"] += absorbed["flops"]
+            w["bytes"] += absorbed["in_bytes"] - w["res_bytes"]
+            absorbed = None
+        if (w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 0
+                and work[i + 1]["in"] == w["out"] and work[i + 1]["in2"] < 0):
+            w2 = work[i + 1]
+            w["name"] += " + " + w2["name"]
+            w["flops"] += w2["flops"]
+            w["bytes"] += w2["out_bytes"]
+            i += 1
+        merged.append((w, t))
+        i += 1
+    return merged
 
 
 KERNEL_NAMES = {"pw": "gemm_tc_kernel / gemm_pair_kernel (1x1 conv)", "fc": "dense_heads_kernel",
@@ -303,35 +339,7 @@ def bench_network(workload, precision, args, rank, world, dev):
     work = plan_work(plan, es)
     classes = {}
     per_step = [t / max(lsteps, 1) for t in lms]
-    merged = []
-    i = 0
-    absorbed = None
-    while i < len(work):
-        w, t = dict(work[i]), per_step[i]
-        if t < 0:
-            # nothing launched (the library reports -1): a bypassed gather, or an 'increase' 1x1 convolution that the next
-            # layer (the projection shortcut it is the residual of) absorbed by K-concatenation (api.cu: plan_kcat)
-            if (w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] >= 0
-                    and work[i + 1]["in2"] == w["out"]):
-                absorbed = w
-            i += 1
-            continue
-        if absorbed is not None:
-            # one GEMM over [x_mid | x_in]: both layers' flops; bytes = both inputs + the output, no residual tensor
-            w["name"] = absorbed["name"] + " (+) " + w["name"]
-            w["flops"] += absorbed["flops"]
-            w["bytes"] += absorbed["in_bytes"] - w["res_bytes"]
-            absorbed = None
-        if w["kind"] == "pw" and i + 1 < len(work) and work[i + 1]["kind"] == "pw" and per_step[i + 1] < 0:
-            # gemm_pair_kernel: this 1x1 convolution and the next one in ONE launch.  The launch's algorithmic work is both
-            # layers' flops and this layer's bytes plus the second layer's OUTPUT only (its input never leaves the SM)
-            w2 = work[i + 1]
-            w["name"] += " + " + w2["name"]
-            w["flops"] += w2["flops"]
-            w["bytes"] += w2["out_bytes"]
-            i += 1
-        merged.append((w, t))
-        i += 1
+    merged = merge_fused_launches(work, per_step)
     for w, t in merged:
         c = classes.setdefault(w["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
         c["ms"] += t

@@ -127,3 +127,40 @@ def test_knn_plan_invariants():
         assert 1 <= per.value <= max(64, 1) and sp.value >= 1
         assert sp.value * per.value >= nb                       # every gallery block belongs to a split
         assert (sp.value - 1) * per.value < nb                  # and no split is empty
+
+
+def test_bench_books_fused_launches_with_their_own_work():
+    """bench.py: per-layer event times (-1 where a layer had no launch of its own) -> one row per launch.  On the
+    ResNet-50 plan with the layers the device plan fuses marked -1: 43 rows (44 launches, the stem's two count once),
+    24 of them 1x1 GEMMs; the flops of the network are conserved, the bytes drop by what the fusions remove, and the
+    1x1 class carries the byte count of the committed benchmark line."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from traffic_from_launches import kcat_absorbed
+    spec = bench.model_spec("resnet50")
+    m = hfr.HfrModel(spec["path"], spec["input"], spec["outputs"], input_hw=spec["hw"], device=None, precision="bf16")
+    layers = m.plan()["layers"]
+    work = bench.plan_work(m.plan(), 2)
+    sub_outs = {L["out"] for L in layers if L["kind"] == "subsample"}
+    t = [1.0] * len(layers)
+    for i, L in enumerate(layers):
+        if L["kind"] == "subsample" or kcat_absorbed(layers, i, sub_outs):
+            t[i] = -1.0
+    for i in range(len(layers) - 1):        # the eight seams: 'reduce' layers fused into the preceding launch
+        A, B = layers[i], layers[i + 1]
+        k0 = layers[i - 1]["cin"] if i > 0 and kcat_absorbed(layers, i - 1, sub_outs) else 0
+        if (A["kind"] == "pw" and B["kind"] == "pw" and B["in"] == A["out"] and B["in2"] < 0 and A["in"] not in sub_outs
+                and t[i] > 0 and pair_config(256 * A["hw_out"][0] * A["hw_out"][1], k0, A["cin"], A["cout"], B["cout"])[0]):
+            t[i + 1] = -1.0
+    merged = bench.merge_fused_launches(work, t)
+    kinds = [w["kind"] for w, _ in merged]
+    assert len(merged) == 43 and kinds.count("pw") == 24 and kinds.count("conv") == 16
+    assert sum(" + " in w["name"] for w, _ in merged) == 8 and sum("(+)" in w["name"] for w, _ in merged) == 4
+    flops_all = sum(w["flops"] for w in work)
+    assert abs(sum(w["flops"] for w, _ in merged) - flops_all) < 1e-6 * flops_all
+    pw_bytes = sum(w["bytes"] for w, _ in merged if w["kind"] == "pw")
+    pw_bytes_unfused = sum(w["bytes"] for w in work if w["kind"] == "pw")
+    assert pw_bytes < 0.75 * pw_bytes_unfused
+    line = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_all.json")))
+    assert line["roofline"]["bound"] == "hbm" and line["kernels"]["pw"]["launches"] == 24
+    assert abs(pw_bytes * 256 / 24 - line["roofline"]["algorithmic_bytes_per_launch"]) < 2
